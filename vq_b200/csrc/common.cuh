@@ -1,0 +1,148 @@
+// common.cuh -- context, error plumbing and pointer classification shared by the
+// kernels of libvqb200.  sm_100a only; there is no CPU path anywhere in this library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vqb200.h"
+
+struct vqb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;   // all kernels
+    bool own_stream = true;
+    cudaStream_t copy_in = nullptr;  // H2D staging for host-pointer calls
+    cudaStream_t copy_out = nullptr; // D2H staging
+    std::string last_error;
+    uint64_t launches = 0;
+    std::mutex mu;                   // handles are immutable, the context is not: serialise calls
+    // pinned mailbox for small per-iteration read-backs
+    void* mailbox = nullptr;
+    size_t mailbox_bytes = 0;
+};
+
+inline int vqb_fail(vqb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    return code;
+}
+
+#define VQB_CUDA(ctx, expr)                                                                    \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return vqb_fail((ctx), VQB_FAILURE, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,   \
+                            cudaGetErrorString(_e));                                           \
+    } while (0)
+
+#define VQB_TRY(expr)                    \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != VQB_SUCCESS) return _s; \
+    } while (0)
+
+// Kernel launch bookkeeping: counts launches (bench.py `gpu_launches`) and surfaces
+// configuration errors immediately.
+#define VQB_LAUNCHED(ctx)                                                                      \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return vqb_fail((ctx), VQB_FAILURE, "%s:%d kernel launch -> %s", __FILE__,         \
+                            __LINE__, cudaGetErrorString(_e));                                 \
+    } while (0)
+
+// true when `p` can be dereferenced by kernels running on ctx->device
+inline bool vqb_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// RAII device buffer tied to a stream-ordered free
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t b) {
+        release();
+        bytes = b;
+        if (b == 0) return cudaSuccess;
+        return cudaMalloc(&p, b);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Brings a caller buffer onto the device if it is a host pointer (synchronous w.r.t. ctx->stream
+// ordering: the copy is enqueued on ctx->stream).  `dev` receives the usable device pointer.
+struct InputView {
+    DevBuf staging;
+    const void* dev = nullptr;
+    bool was_host = false;
+    int bind(vqb_ctx* ctx, const void* p, size_t bytes) {
+        if (bytes == 0) { dev = p; return VQB_SUCCESS; }
+        if (vqb_is_device_ptr(p)) { dev = p; return VQB_SUCCESS; }
+        was_host = true;
+        VQB_CUDA(ctx, staging.alloc(bytes));
+        VQB_CUDA(ctx, cudaMemcpyAsync(staging.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        dev = staging.p;
+        return VQB_SUCCESS;
+    }
+};
+
+// Device-side destination for a caller buffer; `finish` copies back to the host when needed.
+struct OutputView {
+    DevBuf staging;
+    void* dev = nullptr;
+    void* host = nullptr;
+    size_t bytes = 0;
+    int bind(vqb_ctx* ctx, void* p, size_t b) {
+        bytes = b;
+        if (!p || b == 0) { dev = p; return VQB_SUCCESS; }
+        if (vqb_is_device_ptr(p)) { dev = p; return VQB_SUCCESS; }
+        host = p;
+        VQB_CUDA(ctx, staging.alloc(b));
+        dev = staging.p;
+        return VQB_SUCCESS;
+    }
+    int finish(vqb_ctx* ctx) {
+        if (host && bytes)
+            VQB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return VQB_SUCCESS;
+    }
+};
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// internal entry points shared between translation units
+int vqb_pq_assign_exact_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n, size_t dim,
+                               size_t m, size_t k, size_t sub_dim, const float* codebooks,
+                               const int* sub_list_dev, int n_sub, void* codes, uint32_t code_bytes,
+                               size_t code_stride_row, size_t code_stride_sub, __half* recon);
+
+// metric_kind for the exact kernel: the four Distance variants + the training distance
+enum { MK_SQEUCLID = 0, MK_EUCLID = 1, MK_MANHATTAN = 2, MK_COSINE = 3, MK_TRAIN = 4 };

@@ -1,0 +1,191 @@
+// pq_encode.cu -- the immutable ProductQuantizer handle and its batch encode / decode.
+//
+// Reference: ProductQuantizer::quantize / dequantize (src/pq.rs:167-209).  The reference encodes
+// one vector per call and returns the reconstructed centroid values as Vec<f16>; the batch form
+// here returns the same f16 values (recon_out) and/or the compact code indices (codes_out).
+//
+// Host-pointer calls are pipelined in row chunks over three streams (H2D | kernels | D2H) with
+// double-buffered device staging, so the PCIe copies overlap the kernels; device-pointer calls
+// are a single asynchronous launch on the context stream.
+#include "common.cuh"
+
+#include <algorithm>
+
+struct vqb_pq {
+    vqb_ctx* ctx = nullptr;
+    size_t m = 0, k = 0, d = 0;
+    int metric = 0;
+    DevBuf cb;  // [m][k][d] f32
+};
+
+namespace {
+
+// decode: out[row][s*d + t] = f16->f32(f16(codebook[s][code][t]))  (pq.rs:193-195 then :201-209)
+__global__ void k_pq_decode(const void* __restrict__ codes, uint32_t code_bytes, size_t n, int m, int k, int d,
+                            const float* __restrict__ cb, float* __restrict__ out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = n * (size_t)m * d;
+    if (t >= total) return;
+    int comp = (int)(t % d);
+    size_t rs = t / d;  // row * m + s
+    int s = (int)(rs % m);
+    uint32_t c = code_bytes == 1 ? static_cast<const uint8_t*>(codes)[rs]
+               : code_bytes == 2 ? static_cast<const uint16_t*>(codes)[rs]
+                                 : static_cast<const uint32_t*>(codes)[rs];
+    if (c >= (uint32_t)k) c = (uint32_t)k - 1;  // defensive: never read outside the codebook
+    out[t] = __half2float(__float2half_rn(cb[((size_t)s * k + c) * d + comp]));
+}
+
+struct Event {
+    cudaEvent_t e = nullptr;
+    ~Event() { if (e) cudaEventDestroy(e); }
+    cudaError_t make() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+};
+
+int encode_device(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, void* codes, uint32_t code_bytes,
+                  __half* recon, cudaStream_t stream_override = nullptr) {
+    (void)assign_mode;
+    vqb_ctx* ctx = pq->ctx;
+    cudaStream_t saved = ctx->stream;
+    if (stream_override) ctx->stream = stream_override;
+    int rc = vqb_pq_assign_exact_launch(ctx, pq->metric, x, n, pq->m * pq->d, pq->m, pq->k, pq->d,
+                                        pq->cb.as<float>(), nullptr, (int)pq->m, codes, code_bytes,
+                                        /*stride_row=*/pq->m, /*stride_sub=*/1, recon);
+    ctx->stream = saved;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vqb_pq_create(vqb_ctx* ctx, const float* codebooks, size_t m, size_t k, size_t sub_dim, int metric,
+                  vqb_pq** out) {
+    if (!ctx || !out) return VQB_ERR_NULL_PTR;
+    *out = nullptr;
+    if (!codebooks) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null codebooks");
+    if (m == 0 || k == 0 || sub_dim == 0) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "m, k, sub_dim must be > 0");
+    if (metric < 0 || metric > 3) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric %d", metric);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    vqb_pq* p = new vqb_pq();
+    p->ctx = ctx; p->m = m; p->k = k; p->d = sub_dim; p->metric = metric;
+    size_t bytes = m * k * sub_dim * sizeof(float);
+    cudaError_t e = p->cb.alloc(bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->cb.p, codebooks, bytes, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        delete p;
+        return vqb_fail(ctx, VQB_FAILURE, "codebook upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return VQB_SUCCESS;
+}
+
+int vqb_pq_destroy(vqb_pq* pq) {
+    if (!pq) return VQB_ERR_NULL_PTR;
+    cudaStreamSynchronize(pq->ctx->stream);
+    delete pq;
+    return VQB_SUCCESS;
+}
+
+int vqb_pq_codebooks(vqb_pq* pq, float* out) {
+    if (!pq || !out) return VQB_ERR_NULL_PTR;
+    vqb_ctx* ctx = pq->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaMemcpyAsync(out, pq->cb.p, pq->cb.bytes, cudaMemcpyDefault, ctx->stream));
+    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VQB_SUCCESS;
+}
+
+int vqb_pq_encode(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, void* codes_out, uint32_t code_bytes,
+                  uint16_t* recon_out) {
+    if (!pq) return VQB_ERR_NULL_PTR;
+    vqb_ctx* ctx = pq->ctx;
+    if (n == 0) return VQB_SUCCESS;
+    if (!x) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null input");
+    if (!codes_out && !recon_out) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "no output requested");
+    if (codes_out) {
+        if (code_bytes != 1 && code_bytes != 2 && code_bytes != 4)
+            return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "code_bytes must be 1, 2 or 4");
+        if ((code_bytes == 1 && pq->k > 256) || (code_bytes == 2 && pq->k > 65536))
+            return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "k = %zu does not fit %u-byte codes", pq->k, code_bytes);
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t dim = pq->m * pq->d;
+    const bool x_dev = vqb_is_device_ptr(x);
+    const bool c_dev = !codes_out || vqb_is_device_ptr(codes_out);
+    const bool r_dev = !recon_out || vqb_is_device_ptr(recon_out);
+    if (x_dev && c_dev && r_dev)  // all on device: one asynchronous launch
+        return encode_device(pq, x, n, assign_mode, codes_out, code_bytes, reinterpret_cast<__half*>(recon_out));
+
+    // ---- chunked three-stream pipeline ----
+    size_t chunk_rows = std::max<size_t>(1, (size_t(128) << 20) / (dim * sizeof(float)));
+    chunk_rows = std::min(chunk_rows, n);
+    DevBuf xin[2], cst[2], rst[2];
+    Event ev_in[2], ev_comp[2], ev_out[2];
+    for (int b = 0; b < 2; ++b) {
+        if (!x_dev) VQB_CUDA(ctx, xin[b].alloc(chunk_rows * dim * 4));
+        if (codes_out && !c_dev) VQB_CUDA(ctx, cst[b].alloc(chunk_rows * pq->m * code_bytes));
+        if (recon_out && !r_dev) VQB_CUDA(ctx, rst[b].alloc(chunk_rows * dim * 2));
+        VQB_CUDA(ctx, ev_in[b].make()); VQB_CUDA(ctx, ev_comp[b].make()); VQB_CUDA(ctx, ev_out[b].make());
+    }
+    // order the pipeline after whatever is already queued on the context stream
+    Event ev_start; VQB_CUDA(ctx, ev_start.make());
+    VQB_CUDA(ctx, cudaEventRecord(ev_start.e, ctx->stream));
+    VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_start.e, 0));
+    size_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        int b = (int)(c & 1);
+        size_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
+        const float* xd = x + r0 * dim;
+        if (!x_dev) {
+            if (c >= 2) VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_comp[b].e, 0));  // buffer b consumed
+            VQB_CUDA(ctx, cudaMemcpyAsync(xin[b].p, x + r0 * dim, rows * dim * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+            VQB_CUDA(ctx, cudaEventRecord(ev_in[b].e, ctx->copy_in));
+            VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[b].e, 0));
+            xd = xin[b].as<float>();
+        }
+        if (c >= 2) VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[b].e, 0));  // staging b drained
+        void* cd = codes_out ? (c_dev ? (void*)((char*)codes_out + r0 * pq->m * code_bytes) : cst[b].p) : nullptr;
+        __half* rd = recon_out ? (r_dev ? reinterpret_cast<__half*>(recon_out) + r0 * dim : rst[b].as<__half>()) : nullptr;
+        VQB_TRY(encode_device(pq, xd, rows, assign_mode, cd, code_bytes, rd));
+        VQB_CUDA(ctx, cudaEventRecord(ev_comp[b].e, ctx->stream));
+        VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_comp[b].e, 0));
+        if (codes_out && !c_dev)
+            VQB_CUDA(ctx, cudaMemcpyAsync((char*)codes_out + r0 * pq->m * code_bytes, cst[b].p,
+                                          rows * pq->m * code_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (recon_out && !r_dev)
+            VQB_CUDA(ctx, cudaMemcpyAsync(recon_out + r0 * dim, rst[b].p, rows * dim * 2, cudaMemcpyDeviceToHost,
+                                          ctx->copy_out));
+        VQB_CUDA(ctx, cudaEventRecord(ev_out[b].e, ctx->copy_out));
+    }
+    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_in));
+    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    return VQB_SUCCESS;
+}
+
+int vqb_pq_decode(vqb_pq* pq, const void* codes, uint32_t code_bytes, size_t n, float* out) {
+    if (!pq) return VQB_ERR_NULL_PTR;
+    vqb_ctx* ctx = pq->ctx;
+    if (n == 0) return VQB_SUCCESS;
+    if (!codes || !out) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null pointer");
+    if (code_bytes != 1 && code_bytes != 2 && code_bytes != 4)
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "code_bytes must be 1, 2 or 4");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t dim = pq->m * pq->d;
+    InputView in; OutputView ov;
+    VQB_TRY(in.bind(ctx, codes, n * pq->m * code_bytes));
+    VQB_TRY(ov.bind(ctx, out, n * dim * 4));
+    k_pq_decode<<<cdiv(n * dim, 256), 256, 0, ctx->stream>>>(in.dev, code_bytes, n, (int)pq->m, (int)pq->k,
+                                                            (int)pq->d, pq->cb.as<float>(),
+                                                            static_cast<float*>(ov.dev));
+    VQB_LAUNCHED(ctx);
+    VQB_TRY(ov.finish(ctx));
+    if (in.was_host || ov.host) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VQB_SUCCESS;
+}
+
+}  // extern "C"

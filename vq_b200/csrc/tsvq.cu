@@ -1,0 +1,724 @@
+// tsvq.cu -- TSVQ construction (level-synchronous) and batched greedy-descent encoding.
+//
+// Reference: TSVQNode::build (src/tsvq.rs:31-115) is a recursive mean / max-variance-dimension /
+// median split; TSVQNode::find_leaf (:117-132) descends comparing Distance to the two children.
+// Nodes are independent, so all nodes of one depth are processed together here:
+//   mean       sequential f32 column sums over the node's rows in parent order, / n   (vector.rs:332-348)
+//   variance   sequential sum of (x - mean)^2 per column                              (tsvq.rs:47-57)
+//   split dim  arg-max over non-NaN variances, LAST maximum wins                      (tsvq.rs:59-66)
+//   median     exact order statistics of the split column by 4x8-bit radix select     (tsvq.rs:68-81)
+//   partition  stable `<= median` split of the row-id permutation                     (tsvq.rs:84-85)
+// The sums keep the reference's order (one chain per (node, column)), so node centroids and
+// split decisions are bit-identical with the CPU result; rows are streamed through a 4-stage
+// cp.async shared-memory ring so a chain's loads are deep in flight while its adds stay serial.
+//
+// HBM layout: X row-major [n, dim] f32 resident; perm [n] u32 (row ids grouped by node, parent
+// order preserved); node centroids [n_nodes][dim] f32, breadth-first numbering.
+#include "common.cuh"
+#include "distance.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+struct vqb_tsvq {
+    vqb_ctx* ctx = nullptr;
+    size_t dim = 0, n_nodes = 0;
+    int metric = 0;
+    DevBuf cent, left, right;
+    std::vector<int32_t> h_left, h_right, h_split;
+    std::vector<float> h_median;
+    std::vector<uint64_t> h_count;
+    int max_levels = 0;
+};
+
+namespace {
+
+constexpr int CS_THREADS = 256;
+constexpr int CS_SLICE = 32;              // columns per CTA (one accumulating warp)
+constexpr int CS_ROWS = 128;              // rows per ring stage
+constexpr int CS_STAGES = 4;
+constexpr int CS_SMEM = CS_STAGES * CS_ROWS * CS_SLICE * 4;  // 64 KB
+constexpr int PT_THREADS = 256;
+constexpr int PT_STEPS = 8;
+constexpr int PT_CHUNK = PT_THREADS * PT_STEPS;
+
+struct NodeSeg { uint32_t beg, len; };
+struct Chunk { uint32_t node, beg, len; };  // node = index into the level's split list
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// MODE 0: out[node][col] = (sum_rows x) / len          (mean_vector)
+// MODE 1: out[node][col] = sum_rows (x - mean[col])^2   (variances)
+// grid (cdiv(dim, 32), n_nodes); one chain per (node, column), rows streamed through the ring.
+template <int MODE>
+__global__ void __launch_bounds__(CS_THREADS)
+k_colsum(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm,
+         const NodeSeg* __restrict__ nodes, const float* __restrict__ mean /* MODE 1: [n_nodes][dim] */,
+         float* __restrict__ out, int vec_ok) {
+    extern __shared__ __align__(16) float ring[];  // [stage][row][32]
+    const NodeSeg ns = nodes[blockIdx.y];
+    const int col0 = blockIdx.x * CS_SLICE;
+    const int ncol = min(CS_SLICE, dim - col0);
+    const int tid = threadIdx.x;
+    const int n_tiles = (int)((ns.len + CS_ROWS - 1) / CS_ROWS);
+    const uint32_t* ids = perm + ns.beg;
+
+    auto issue = [&](int tile) {
+        if (tile < n_tiles) {
+            float* st = ring + (size_t)(tile % CS_STAGES) * CS_ROWS * CS_SLICE;
+            const int r0 = tile * CS_ROWS;
+            const int rows = min(CS_ROWS, (int)ns.len - r0);
+            if (vec_ok && ncol == CS_SLICE) {
+                // 8 threads x 16 B cover one 128 B row slice; 256 threads cover 32 rows per pass
+                for (int r = tid >> 3; r < rows; r += CS_THREADS / 8) {
+                    const float* src = x + (size_t)ids[r0 + r] * dim + col0 + (tid & 7) * 4;
+                    cp_async16(st + r * CS_SLICE + (tid & 7) * 4, src);
+                }
+            } else {
+                for (int e = tid; e < rows * CS_SLICE; e += CS_THREADS) {
+                    int r = e / CS_SLICE, c = e % CS_SLICE;
+                    if (c < ncol) cp_async4(st + r * CS_SLICE + c, x + (size_t)ids[r0 + r] * dim + col0 + c);
+                }
+            }
+        }
+        cp_async_commit();  // one group per call keeps the wait arithmetic uniform
+    };
+
+    float acc = 0.0f, mu = 0.0f;
+    if (MODE == 1 && tid < ncol) mu = mean[(size_t)blockIdx.y * dim + col0 + tid];
+#pragma unroll
+    for (int s = 0; s < CS_STAGES - 1; ++s) issue(s);
+    for (int t = 0; t < n_tiles; ++t) {
+        issue(t + CS_STAGES - 1);
+        cp_async_wait<CS_STAGES - 1>();
+        __syncthreads();
+        if (tid < ncol) {
+            const float* st = ring + (size_t)(t % CS_STAGES) * CS_ROWS * CS_SLICE + tid;
+            const int rows = min(CS_ROWS, (int)ns.len - t * CS_ROWS);
+            if (MODE == 0) {
+#pragma unroll 8
+                for (int r = 0; r < rows; ++r) acc = __fadd_rn(acc, st[r * CS_SLICE]);
+            } else {
+#pragma unroll 8
+                for (int r = 0; r < rows; ++r) {
+                    float df = __fsub_rn(st[r * CS_SLICE], mu);
+                    acc = __fadd_rn(acc, __fmul_rn(df, df));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < ncol) {
+        if (MODE == 0) acc = __fdiv_rn(acc, __uint2float_rn(ns.len));  // `vectors.len()` as f32
+        out[(size_t)blockIdx.y * dim + col0 + tid] = acc;
+    }
+}
+
+// arg-max over non-NaN variances, last maximum wins (Iterator::max_by); all NaN -> 0.  One CTA per node.
+__global__ void __launch_bounds__(256) k_argmax_last(const float* __restrict__ var, int dim, int* __restrict__ split_dim) {
+    __shared__ float sv[256];
+    __shared__ int si[256];
+    const float* v = var + (size_t)blockIdx.x * dim;
+    float best = 0.f; int bi = -1;
+    // each thread scans a contiguous range so that "last maximum" is preserved by an ordered merge
+    int per = (dim + 255) / 256;
+    int b = threadIdx.x * per, e = min(dim, b + per);
+    for (int i = b; i < e; ++i) {
+        float f = v[i];
+        if (isnan(f)) continue;
+        if (bi < 0 || !(f < best)) { best = f; bi = i; }
+    }
+    sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float g = 0.f; int gi = -1;
+        for (int t = 0; t < 256; ++t) {
+            if (si[t] < 0) continue;
+            if (gi < 0 || !(sv[t] < g)) { g = sv[t]; gi = si[t]; }
+        }
+        split_dim[blockIdx.x] = gi < 0 ? 0 : gi;
+    }
+}
+
+__device__ __forceinline__ uint32_t order_key(float f) {  // unsigned order == f32::total_cmp order
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(b);
+}
+
+// vals[i] = x[perm[i]][split_dim[node]] for every position of every split node; counts non-NaN.
+__global__ void __launch_bounds__(PT_THREADS)
+k_gather_split(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm,
+               const Chunk* __restrict__ chunks, const int* __restrict__ split_dim,
+               float* __restrict__ vals, uint32_t* __restrict__ n_valid) {
+    const Chunk ch = chunks[blockIdx.x];
+    const int sd = split_dim[ch.node];
+    uint32_t local = 0;
+    for (uint32_t i = threadIdx.x; i < ch.len; i += PT_THREADS) {
+        float v = x[(size_t)perm[ch.beg + i] * dim + sd];
+        vals[ch.beg + i] = v;
+        local += !isnan(v);
+    }
+    // block reduction
+    __shared__ uint32_t red[PT_THREADS / 32];
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) t += red[w];
+        if (t) atomicAdd(&n_valid[ch.node], t);
+    }
+}
+
+struct SelState { uint32_t prefix[2]; uint32_t rem[2]; };
+
+__global__ void k_select_init(const uint32_t* __restrict__ n_valid, SelState* __restrict__ st, int n_nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint32_t nv = n_valid[i];
+    st[i].prefix[0] = st[i].prefix[1] = 0;
+    if (nv == 0) { st[i].rem[0] = st[i].rem[1] = 0; return; }
+    st[i].rem[0] = (nv % 2 == 0) ? nv / 2 - 1 : nv / 2;  // tsvq.rs:77-81
+    st[i].rem[1] = nv / 2;
+}
+
+// histogram of digit (key >> shift) & 255 over the keys that share each target's current prefix
+__global__ void __launch_bounds__(PT_THREADS)
+k_select_hist(const float* __restrict__ vals, const Chunk* __restrict__ chunks, const SelState* __restrict__ st,
+              int shift, uint32_t* __restrict__ hist /* [n_nodes][2][256] */) {
+    __shared__ uint32_t h[2][256];
+    h[0][threadIdx.x] = 0; h[1][threadIdx.x] = 0;
+    __syncthreads();
+    const Chunk ch = chunks[blockIdx.x];
+    const SelState s = st[ch.node];
+    const uint32_t hi_mask = shift >= 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (uint32_t i = threadIdx.x; i < ch.len; i += PT_THREADS) {
+        float v = vals[ch.beg + i];
+        if (isnan(v)) continue;  // tsvq.rs:71
+        uint32_t key = order_key(v), dgt = (key >> shift) & 255u;
+        if ((key & hi_mask) == (s.prefix[0] & hi_mask)) atomicAdd(&h[0][dgt], 1u);
+        if ((key & hi_mask) == (s.prefix[1] & hi_mask)) atomicAdd(&h[1][dgt], 1u);
+    }
+    __syncthreads();
+    uint32_t a = h[0][threadIdx.x], b = h[1][threadIdx.x];
+    if (a) atomicAdd(&hist[((size_t)ch.node * 2 + 0) * 256 + threadIdx.x], a);
+    if (b) atomicAdd(&hist[((size_t)ch.node * 2 + 1) * 256 + threadIdx.x], b);
+}
+
+__global__ void k_select_pick(SelState* __restrict__ st, uint32_t* __restrict__ hist, int shift, int n_nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes * 2) return;
+    int node = i >> 1, w = i & 1;
+    uint32_t* h = hist + (size_t)i * 256;
+    uint32_t rem = st[node].rem[w], acc = 0;
+    int dg = 255;
+    for (int b = 0; b < 256; ++b) {
+        uint32_t c = h[b];
+        if (acc + c > rem) { dg = b; break; }
+        acc += c;
+    }
+    st[node].rem[w] = rem - acc;
+    st[node].prefix[w] |= (uint32_t)dg << shift;
+    for (int b = 0; b < 256; ++b) h[b] = 0;  // ready for the next pass
+}
+
+__global__ void k_select_finish(const SelState* __restrict__ st, const uint32_t* __restrict__ n_valid,
+                                float* __restrict__ median, int n_nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint32_t nv = n_valid[i];
+    if (nv == 0) { median[i] = nanf(""); return; }
+    float a = key_to_float(st[i].prefix[0]), b = key_to_float(st[i].prefix[1]);
+    median[i] = (nv % 2 == 0) ? __fdiv_rn(__fadd_rn(a, b), 2.0f) : b;
+}
+
+// stable partition, pass 1: number of `<= median` elements per chunk
+__global__ void __launch_bounds__(PT_THREADS)
+k_part_count(const float* __restrict__ vals, const Chunk* __restrict__ chunks, const float* __restrict__ median,
+             uint32_t* __restrict__ chunk_left) {
+    const Chunk ch = chunks[blockIdx.x];
+    const float med = median[ch.node];
+    uint32_t local = 0;
+    for (uint32_t i = threadIdx.x; i < ch.len; i += PT_THREADS) local += (vals[ch.beg + i] <= med);
+    __shared__ uint32_t red[PT_THREADS / 32];
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) t += red[w];
+        chunk_left[blockIdx.x] = t;
+    }
+}
+
+// pass 2 (one thread per node): exclusive scan of its chunks' left counts; emits the node's left total
+__global__ void k_part_scan(const uint32_t* __restrict__ node_chunk_beg, uint32_t* __restrict__ chunk_left,
+                            uint32_t* __restrict__ node_left, int n_nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint32_t acc = 0;
+    for (uint32_t c = node_chunk_beg[i]; c < node_chunk_beg[i + 1]; ++c) {
+        uint32_t v = chunk_left[c];
+        chunk_left[c] = acc;
+        acc += v;
+    }
+    node_left[i] = acc;
+}
+
+// pass 3: stable scatter into perm_out (order inside each side preserved, tsvq.rs:84-85)
+__global__ void __launch_bounds__(PT_THREADS)
+k_part_scatter(const float* __restrict__ vals, const uint32_t* __restrict__ perm, const Chunk* __restrict__ chunks,
+               const NodeSeg* __restrict__ nodes, const float* __restrict__ median,
+               const uint32_t* __restrict__ chunk_left, const uint32_t* __restrict__ node_left,
+               uint32_t* __restrict__ perm_out) {
+    __shared__ uint32_t wl[PT_THREADS / 32];
+    __shared__ uint32_t run_l, run_r;
+    const Chunk ch = chunks[blockIdx.x];
+    const NodeSeg ns = nodes[ch.node];
+    const float med = median[ch.node];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nl_total = node_left[ch.node];
+    if (threadIdx.x == 0) {
+        run_l = chunk_left[blockIdx.x];
+        run_r = (ch.beg - ns.beg) - chunk_left[blockIdx.x];  // elements before this chunk that went right
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < ch.len; base += PT_THREADS) {
+        uint32_t i = base + threadIdx.x;
+        bool live = i < ch.len;
+        bool goes_left = live && (vals[ch.beg + i] <= med);
+        uint32_t bl = __ballot_sync(0xFFFFFFFFu, goes_left);
+        if (lane == 0) wl[warp] = __popc(bl);
+        __syncthreads();
+        uint32_t before_l = 0;
+        for (int w = 0; w < warp; ++w) before_l += wl[w];
+        uint32_t lrank = before_l + __popc(bl & ((1u << lane) - 1u));
+        uint32_t pos_in_step = threadIdx.x;             // live lanes are a prefix of the step
+        uint32_t rrank = pos_in_step - lrank;           // earlier elements of this step that went right
+        if (live) {
+            uint32_t id = perm[ch.beg + i];
+            if (goes_left) perm_out[ns.beg + run_l + lrank] = id;
+            else perm_out[ns.beg + nl_total + run_r + rrank] = id;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tl = 0;
+            for (int w = 0; w < PT_THREADS / 32; ++w) tl += wl[w];
+            uint32_t step = min((uint32_t)PT_THREADS, ch.len - base);
+            run_l += tl;
+            run_r += step - tl;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- encode: one warp per vector, the two child distances on the two half-warps -----------------
+// Lane l of a half-warp owns elements i == l (mod 16), i.e. exactly one AVX-512 lane of hsdlib's
+// kernels, and the half-warp shuffle tree repeats _mm512_reduce_add_ps.
+__device__ __forceinline__ float half_reduce16(float v) {
+    v = __fadd_rn(v, __shfl_down_sync(0xFFFFFFFFu, v, 8, 16));
+    v = __fadd_rn(v, __shfl_down_sync(0xFFFFFFFFu, v, 4, 16));
+    v = __fadd_rn(v, __shfl_down_sync(0xFFFFFFFFu, v, 2, 16));
+    v = __fadd_rn(v, __shfl_down_sync(0xFFFFFFFFu, v, 1, 16));
+    return v;  // valid on lane 0 of the half-warp
+}
+
+template <int METRIC>
+__device__ __forceinline__ float pair_distance_halfwarp(const float* __restrict__ v, const float* __restrict__ c,
+                                                        int n, int hl) {
+    const int nb = n & ~15;
+    PtrAcc pa{v}, pb{c};
+    float result = 0.f;
+    if (METRIC == VQB_COSINE) {
+        float d = 0.f, xa = 0.f, xb = 0.f;
+        for (int i = hl; i < nb; i += 16) {
+            float u = v[i], w = c[i];
+            d = __fmaf_rn(u, w, d); xa = __fmaf_rn(u, u, xa); xb = __fmaf_rn(w, w, xb);
+        }
+        d = half_reduce16(d); xa = half_reduce16(xa); xb = half_reduce16(xb);
+        if (hl == 0) {
+            bool tail_ok = true;
+            if (n < 16) { d = xa = xb = 0.f; }
+            for (int i = nb; i < n; ++i) {
+                float u = v[i], w = c[i];
+                if (vqb_bad(u) || vqb_bad(w)) { tail_ok = false; break; }
+                d = __fadd_rn(d, __fmul_rn(u, w));
+                xa = __fadd_rn(xa, __fmul_rn(u, u));
+                xb = __fadd_rn(xb, __fmul_rn(w, w));
+            }
+            bool ok = tail_ok;
+            float sim = 0.f;
+            if (ok) sim = hsd_cosine_from_sums(d, xa, xb, __fsqrt_rn(xa), __fsqrt_rn(xb), ok);
+            result = ok ? __fsub_rn(1.0f, sim) : rust_cos<0>(pa, pb, n);
+            if (n == 0) result = 0.f;
+        }
+    } else {
+        float acc = 0.f;
+        for (int i = hl; i < nb; i += 16) {
+            float df = __fsub_rn(v[i], c[i]);
+            acc = (METRIC == VQB_MANHATTAN) ? __fadd_rn(acc, fabsf(df)) : __fmaf_rn(df, df, acc);
+        }
+        acc = half_reduce16(acc);
+        if (hl == 0) {
+            bool ok = true;
+            if (n < 16) acc = 0.f;
+            for (int i = nb; i < n; ++i) {
+                float u = v[i], w = c[i];
+                if (vqb_bad(u) || vqb_bad(w)) { ok = false; break; }
+                float df = __fsub_rn(u, w);
+                acc = (METRIC == VQB_MANHATTAN) ? __fadd_rn(acc, fabsf(df)) : __fadd_rn(acc, __fmul_rn(df, df));
+            }
+            if (ok && vqb_bad(acc)) ok = false;
+            if (!ok) acc = (METRIC == VQB_MANHATTAN) ? rust_l1<0>(pa, pb, n) : dist2_seq<0>(pa, pb, n);
+            result = (METRIC == VQB_EUCLIDEAN) ? __fsqrt_rn(acc) : acc;
+        }
+    }
+    return result;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+k_tsvq_encode(const float* __restrict__ x, size_t n, int dim, const float* __restrict__ cent,
+              const int* __restrict__ left, const int* __restrict__ right, uint32_t* __restrict__ leaf_out,
+              __half* __restrict__ recon) {
+    const size_t row = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= n) return;  // warp-uniform
+    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const float* v = x + row * (size_t)dim;
+    int node = 0;
+    for (;;) {
+        int l = left[node], r = right[node];
+        if (l >= 0 && r >= 0) {
+            const float* c = cent + (size_t)(half ? r : l) * dim;
+            float dmine = pair_distance_halfwarp<METRIC>(v, c, dim, hl);
+            float dl = __shfl_sync(0xFFFFFFFFu, dmine, 0), dr = __shfl_sync(0xFFFFFFFFu, dmine, 16);
+            node = (dl <= dr) ? l : r;  // tsvq.rs:122
+        } else if (l >= 0) node = l;
+        else if (r >= 0) node = r;
+        else break;
+    }
+    if (leaf_out && lane == 0) leaf_out[row] = (uint32_t)node;
+    if (recon) {  // tsvq.rs:248-254
+        const float* c = cent + (size_t)node * dim;
+        __half* o = recon + row * (size_t)dim;
+        for (int i = lane; i < dim; i += 32) o[i] = __float2half_rn(c[i]);
+    }
+}
+
+struct LevelNode { uint32_t id, beg, len, depth_left; };
+
+}  // namespace
+
+extern "C" {
+
+int vqb_tsvq_destroy(vqb_tsvq* t) {
+    if (!t) return VQB_ERR_NULL_PTR;
+    cudaStreamSynchronize(t->ctx->stream);
+    delete t;
+    return VQB_SUCCESS;
+}
+
+int vqb_tsvq_num_nodes(vqb_tsvq* t, size_t* n_nodes, size_t* dim) {
+    if (!t) return VQB_ERR_NULL_PTR;
+    if (n_nodes) *n_nodes = t->n_nodes;
+    if (dim) *dim = t->dim;
+    return VQB_SUCCESS;
+}
+
+int vqb_tsvq_export(vqb_tsvq* t, float* centroids, int32_t* left, int32_t* right, int32_t* split_dim,
+                    float* median, uint64_t* count) {
+    if (!t) return VQB_ERR_NULL_PTR;
+    vqb_ctx* ctx = t->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (centroids) {
+        VQB_CUDA(ctx, cudaMemcpyAsync(centroids, t->cent.p, t->n_nodes * t->dim * 4, cudaMemcpyDefault, ctx->stream));
+        VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (left) std::memcpy(left, t->h_left.data(), t->n_nodes * 4);
+    if (right) std::memcpy(right, t->h_right.data(), t->n_nodes * 4);
+    if (split_dim) std::memcpy(split_dim, t->h_split.data(), t->n_nodes * 4);
+    if (median) std::memcpy(median, t->h_median.data(), t->n_nodes * 4);
+    if (count) std::memcpy(count, t->h_count.data(), t->n_nodes * 8);
+    return VQB_SUCCESS;
+}
+
+int vqb_tsvq_create(vqb_ctx* ctx, const float* centroids, const int32_t* left, const int32_t* right,
+                    size_t n_nodes, size_t dim, int metric, vqb_tsvq** out) {
+    if (!ctx || !out) return VQB_ERR_NULL_PTR;
+    *out = nullptr;
+    if (!centroids || !left || !right) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null tree arrays");
+    if (n_nodes == 0 || dim == 0) return vqb_fail(ctx, VQB_ERR_EMPTY_INPUT, "empty tree");
+    if (metric < 0 || metric > 3) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric %d", metric);
+    if (vqb_is_device_ptr(left) || vqb_is_device_ptr(right))
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "left/right must be host arrays");
+    for (size_t i = 0; i < n_nodes; ++i)  // children must point forward (breadth-first numbering): no cycles
+        if ((left[i] >= 0 && ((size_t)left[i] <= i || (size_t)left[i] >= n_nodes)) ||
+            (right[i] >= 0 && ((size_t)right[i] <= i || (size_t)right[i] >= n_nodes)))
+            return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "node %zu has an invalid child", i);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    vqb_tsvq* t = new vqb_tsvq();
+    t->ctx = ctx; t->dim = dim; t->n_nodes = n_nodes; t->metric = metric;
+    t->h_left.assign(left, left + n_nodes);
+    t->h_right.assign(right, right + n_nodes);
+    t->h_split.assign(n_nodes, -1);
+    t->h_median.assign(n_nodes, std::nanf(""));
+    t->h_count.assign(n_nodes, 0);
+    cudaError_t e = t->cent.alloc(n_nodes * dim * 4);
+    if (e == cudaSuccess) e = t->left.alloc(n_nodes * 4);
+    if (e == cudaSuccess) e = t->right.alloc(n_nodes * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->cent.p, centroids, n_nodes * dim * 4, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->left.p, left, n_nodes * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->right.p, right, n_nodes * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { delete t; return vqb_fail(ctx, VQB_FAILURE, "tree upload failed: %s", cudaGetErrorString(e)); }
+    *out = t;
+    return VQB_SUCCESS;
+}
+
+int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t max_depth, int metric,
+                   vqb_tsvq** out) {
+    if (!ctx || !out) return VQB_ERR_NULL_PTR;
+    *out = nullptr;
+    if (n == 0) return vqb_fail(ctx, VQB_ERR_EMPTY_INPUT, "Empty input: at least one vector is required");
+    if (!x) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null data pointer");
+    if (dim == 0) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "dimension must be > 0");
+    if (metric < 0 || metric > 3) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric %d", metric);
+    if (n > 0xFFFFFFF0ull || dim > (size_t)INT32_MAX) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "shape too large");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    InputView xin;
+    VQB_TRY(xin.bind(ctx, x, n * dim * 4));
+    const float* xd = static_cast<const float*>(xin.dev);
+    const int vec_ok = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(xd) & 15) == 0);
+    VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+    VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+
+    DevBuf perm_a, perm_b, vals;
+    VQB_CUDA(ctx, perm_a.alloc(n * 4));
+    VQB_CUDA(ctx, perm_b.alloc(n * 4));
+    VQB_CUDA(ctx, vals.alloc(n * 4));
+    {
+        std::vector<uint32_t> ident(n);
+        for (size_t i = 0; i < n; ++i) ident[i] = (uint32_t)i;
+        VQB_CUDA(ctx, cudaMemcpyAsync(perm_a.p, ident.data(), n * 4, cudaMemcpyHostToDevice, st));
+        VQB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    uint32_t* perm = perm_a.as<uint32_t>();
+    uint32_t* perm_next = perm_b.as<uint32_t>();
+
+    std::vector<int32_t> h_left, h_right, h_split;
+    std::vector<float> h_median;
+    std::vector<uint64_t> h_count;
+    std::vector<std::vector<float>> level_cent;  // host copies per level (<= a few MB each)
+    std::vector<LevelNode> level{{0u, 0u, (uint32_t)n, (uint32_t)std::min<size_t>(max_depth, 0xFFFFFFFFu)}};
+    h_left.push_back(-1); h_right.push_back(-1); h_split.push_back(-1);
+    h_median.push_back(std::nanf("")); h_count.push_back(n);
+    size_t n_nodes = 1;
+
+    while (!level.empty()) {
+        const size_t ln = level.size();
+        // ---- means of every node of the level (tsvq.rs:36) ----
+        std::vector<NodeSeg> segs(ln);
+        for (size_t i = 0; i < ln; ++i) segs[i] = {level[i].beg, level[i].len};
+        DevBuf d_segs, d_mean;
+        VQB_CUDA(ctx, d_segs.alloc(ln * sizeof(NodeSeg)));
+        VQB_CUDA(ctx, d_mean.alloc(ln * dim * 4));
+        VQB_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), ln * sizeof(NodeSeg), cudaMemcpyHostToDevice, st));
+        dim3 gcs(cdiv(dim, CS_SLICE), (unsigned)ln);
+        if (gcs.y > 65535) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "too many nodes on one level");
+        k_colsum<0><<<gcs, CS_THREADS, CS_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr,
+                                                     d_mean.as<float>(), vec_ok);
+        VQB_LAUNCHED(ctx);
+        level_cent.emplace_back(ln * dim);
+        VQB_CUDA(ctx, cudaMemcpyAsync(level_cent.back().data(), d_mean.p, ln * dim * 4, cudaMemcpyDeviceToHost, st));
+
+        // ---- nodes that try to split (tsvq.rs:38) ----
+        std::vector<uint32_t> split_idx;
+        for (size_t i = 0; i < ln; ++i)
+            if (level[i].depth_left > 0 && level[i].len > 1) split_idx.push_back((uint32_t)i);
+        if (split_idx.empty()) { VQB_CUDA(ctx, cudaStreamSynchronize(st)); break; }
+        const size_t sn = split_idx.size();
+        std::vector<NodeSeg> ssegs(sn);
+        std::vector<Chunk> chunks;
+        std::vector<uint32_t> node_chunk_beg(sn + 1);
+        for (size_t q = 0; q < sn; ++q) {
+            const LevelNode& nd = level[split_idx[q]];
+            ssegs[q] = {nd.beg, nd.len};
+            node_chunk_beg[q] = (uint32_t)chunks.size();
+            for (uint32_t o = 0; o < nd.len; o += PT_CHUNK)
+                chunks.push_back({(uint32_t)q, nd.beg + o, std::min<uint32_t>(PT_CHUNK, nd.len - o)});
+        }
+        node_chunk_beg[sn] = (uint32_t)chunks.size();
+        const size_t cn = chunks.size();
+        DevBuf d_ssegs, d_smean, d_var, d_sd, d_chunks, d_ncb, d_nvalid, d_sel, d_hist, d_median, d_cleft, d_nleft;
+        VQB_CUDA(ctx, d_ssegs.alloc(sn * sizeof(NodeSeg)));
+        VQB_CUDA(ctx, d_smean.alloc(sn * dim * 4));
+        VQB_CUDA(ctx, d_var.alloc(sn * dim * 4));
+        VQB_CUDA(ctx, d_sd.alloc(sn * 4));
+        VQB_CUDA(ctx, d_chunks.alloc(cn * sizeof(Chunk)));
+        VQB_CUDA(ctx, d_ncb.alloc((sn + 1) * 4));
+        VQB_CUDA(ctx, d_nvalid.alloc(sn * 4));
+        VQB_CUDA(ctx, d_sel.alloc(sn * sizeof(SelState)));
+        VQB_CUDA(ctx, d_hist.alloc(sn * 2 * 256 * 4));
+        VQB_CUDA(ctx, d_median.alloc(sn * 4));
+        VQB_CUDA(ctx, d_cleft.alloc(cn * 4));
+        VQB_CUDA(ctx, d_nleft.alloc(sn * 4));
+        VQB_CUDA(ctx, cudaMemcpyAsync(d_ssegs.p, ssegs.data(), sn * sizeof(NodeSeg), cudaMemcpyHostToDevice, st));
+        VQB_CUDA(ctx, cudaMemcpyAsync(d_chunks.p, chunks.data(), cn * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+        VQB_CUDA(ctx, cudaMemcpyAsync(d_ncb.p, node_chunk_beg.data(), (sn + 1) * 4, cudaMemcpyHostToDevice, st));
+        // compact the means of the splitting nodes (device-to-device row copies)
+        for (size_t q = 0; q < sn; ++q)
+            VQB_CUDA(ctx, cudaMemcpyAsync(d_smean.as<float>() + q * dim, d_mean.as<float>() + (size_t)split_idx[q] * dim,
+                                          dim * 4, cudaMemcpyDeviceToDevice, st));
+        VQB_CUDA(ctx, cudaMemsetAsync(d_nvalid.p, 0, sn * 4, st));
+        VQB_CUDA(ctx, cudaMemsetAsync(d_hist.p, 0, sn * 2 * 256 * 4, st));
+
+        dim3 gvs(cdiv(dim, CS_SLICE), (unsigned)sn);
+        k_colsum<1><<<gvs, CS_THREADS, CS_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(),
+                                                     d_var.as<float>(), vec_ok);
+        VQB_LAUNCHED(ctx);
+        k_argmax_last<<<(unsigned)sn, 256, 0, st>>>(d_var.as<float>(), (int)dim, d_sd.as<int>());
+        VQB_LAUNCHED(ctx);
+        k_gather_split<<<(unsigned)cn, PT_THREADS, 0, st>>>(xd, (int)dim, perm, d_chunks.as<Chunk>(), d_sd.as<int>(),
+                                                           vals.as<float>(), d_nvalid.as<uint32_t>());
+        VQB_LAUNCHED(ctx);
+        k_select_init<<<cdiv(sn, 128), 128, 0, st>>>(d_nvalid.as<uint32_t>(), d_sel.as<SelState>(), (int)sn);
+        VQB_LAUNCHED(ctx);
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            k_select_hist<<<(unsigned)cn, PT_THREADS, 0, st>>>(vals.as<float>(), d_chunks.as<Chunk>(),
+                                                              d_sel.as<SelState>(), shift, d_hist.as<uint32_t>());
+            VQB_LAUNCHED(ctx);
+            k_select_pick<<<cdiv(sn * 2, 64), 64, 0, st>>>(d_sel.as<SelState>(), d_hist.as<uint32_t>(), shift, (int)sn);
+            VQB_LAUNCHED(ctx);
+        }
+        k_select_finish<<<cdiv(sn, 128), 128, 0, st>>>(d_sel.as<SelState>(), d_nvalid.as<uint32_t>(),
+                                                      d_median.as<float>(), (int)sn);
+        VQB_LAUNCHED(ctx);
+        k_part_count<<<(unsigned)cn, PT_THREADS, 0, st>>>(vals.as<float>(), d_chunks.as<Chunk>(), d_median.as<float>(),
+                                                         d_cleft.as<uint32_t>());
+        VQB_LAUNCHED(ctx);
+        k_part_scan<<<cdiv(sn, 64), 64, 0, st>>>(d_ncb.as<uint32_t>(), d_cleft.as<uint32_t>(), d_nleft.as<uint32_t>(), (int)sn);
+        VQB_LAUNCHED(ctx);
+        // rows of nodes that do not split keep their place: start from a copy of the permutation
+        VQB_CUDA(ctx, cudaMemcpyAsync(perm_next, perm, n * 4, cudaMemcpyDeviceToDevice, st));
+        k_part_scatter<<<(unsigned)cn, PT_THREADS, 0, st>>>(vals.as<float>(), perm, d_chunks.as<Chunk>(),
+                                                           d_ssegs.as<NodeSeg>(), d_median.as<float>(),
+                                                           d_cleft.as<uint32_t>(), d_nleft.as<uint32_t>(), perm_next);
+        VQB_LAUNCHED(ctx);
+
+        std::vector<uint32_t> nleft(sn), nvalid(sn);
+        std::vector<int> sd(sn);
+        std::vector<float> med(sn);
+        VQB_CUDA(ctx, cudaMemcpyAsync(nleft.data(), d_nleft.p, sn * 4, cudaMemcpyDeviceToHost, st));
+        VQB_CUDA(ctx, cudaMemcpyAsync(nvalid.data(), d_nvalid.p, sn * 4, cudaMemcpyDeviceToHost, st));
+        VQB_CUDA(ctx, cudaMemcpyAsync(sd.data(), d_sd.p, sn * 4, cudaMemcpyDeviceToHost, st));
+        VQB_CUDA(ctx, cudaMemcpyAsync(med.data(), d_median.p, sn * 4, cudaMemcpyDeviceToHost, st));
+        VQB_CUDA(ctx, cudaStreamSynchronize(st));
+
+        std::vector<LevelNode> next;
+        for (size_t q = 0; q < sn; ++q) {
+            const LevelNode nd = level[split_idx[q]];
+            if (nvalid[q] == 0)  // every split coordinate is NaN: the reference indexes an empty Vec and panics
+                return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "node %u: split column holds only NaN", nd.id);
+            h_split[nd.id] = sd[q];
+            h_median[nd.id] = med[q];
+            uint32_t nl = nleft[q], nr = nd.len - nl;
+            if (nl > 0 && nl < nd.len) {  // tsvq.rs:88
+                h_left[nd.id] = (int32_t)n_nodes;
+                next.push_back({(uint32_t)n_nodes, nd.beg, nl, nd.depth_left - 1});
+                h_left.push_back(-1); h_right.push_back(-1); h_split.push_back(-1);
+                h_median.push_back(std::nanf("")); h_count.push_back(nl);
+                ++n_nodes;
+            }
+            if (nr > 0 && nr < nd.len) {  // tsvq.rs:99
+                h_right[nd.id] = (int32_t)n_nodes;
+                next.push_back({(uint32_t)n_nodes, nd.beg + nl, nr, nd.depth_left - 1});
+                h_left.push_back(-1); h_right.push_back(-1); h_split.push_back(-1);
+                h_median.push_back(std::nanf("")); h_count.push_back(nr);
+                ++n_nodes;
+            }
+        }
+        std::swap(perm, perm_next);
+        level.swap(next);
+    }
+    VQB_CUDA(ctx, cudaStreamSynchronize(st));
+
+    // assemble the breadth-first centroid table (levels were produced in id order)
+    std::vector<float> cent(n_nodes * dim);
+    size_t off = 0;
+    for (auto& lc : level_cent) { std::memcpy(cent.data() + off, lc.data(), lc.size() * 4); off += lc.size(); }
+    if (off != n_nodes * dim) return vqb_fail(ctx, VQB_FAILURE, "internal: centroid table size mismatch");
+
+    vqb_tsvq* t = new vqb_tsvq();
+    t->ctx = ctx; t->dim = dim; t->n_nodes = n_nodes; t->metric = metric;
+    t->h_left = h_left; t->h_right = h_right; t->h_split = h_split; t->h_median = h_median; t->h_count = h_count;
+    cudaError_t e = t->cent.alloc(n_nodes * dim * 4);
+    if (e == cudaSuccess) e = t->left.alloc(n_nodes * 4);
+    if (e == cudaSuccess) e = t->right.alloc(n_nodes * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->cent.p, cent.data(), n_nodes * dim * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->left.p, h_left.data(), n_nodes * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->right.p, h_right.data(), n_nodes * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { delete t; return vqb_fail(ctx, VQB_FAILURE, "tree upload failed: %s", cudaGetErrorString(e)); }
+    *out = t;
+    return VQB_SUCCESS;
+}
+
+int vqb_tsvq_encode(vqb_tsvq* t, const float* x, size_t n, uint32_t* leaf_out, uint16_t* recon_out) {
+    if (!t) return VQB_ERR_NULL_PTR;
+    vqb_ctx* ctx = t->ctx;
+    if (n == 0) return VQB_SUCCESS;
+    if (!x) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null input");
+    if (!leaf_out && !recon_out) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "no output requested");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t dim = t->dim;
+    // host inputs/outputs are processed in row chunks so arbitrarily large batches fit
+    const bool all_dev = vqb_is_device_ptr(x) && (!leaf_out || vqb_is_device_ptr(leaf_out)) &&
+                         (!recon_out || vqb_is_device_ptr(recon_out));
+    size_t chunk = all_dev ? n : std::max<size_t>(1, (size_t(256) << 20) / (dim * 4));
+    for (size_t r0 = 0; r0 < n; r0 += chunk) {
+        size_t rows = std::min(chunk, n - r0);
+        InputView in; OutputView lo, ro;
+        VQB_TRY(in.bind(ctx, x + r0 * dim, rows * dim * 4));
+        VQB_TRY(lo.bind(ctx, leaf_out ? leaf_out + r0 : nullptr, rows * 4));
+        VQB_TRY(ro.bind(ctx, recon_out ? recon_out + r0 * dim : nullptr, rows * dim * 2));
+        const float* xd = static_cast<const float*>(in.dev);
+        uint32_t* ld = static_cast<uint32_t*>(lo.dev);
+        __half* rd = static_cast<__half*>(ro.dev);
+        unsigned grid = cdiv(rows, 8);
+        switch (t->metric) {
+            case VQB_SQUARED_EUCLIDEAN:
+                k_tsvq_encode<VQB_SQUARED_EUCLIDEAN><<<grid, 256, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd); break;
+            case VQB_EUCLIDEAN:
+                k_tsvq_encode<VQB_EUCLIDEAN><<<grid, 256, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd); break;
+            case VQB_MANHATTAN:
+                k_tsvq_encode<VQB_MANHATTAN><<<grid, 256, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd); break;
+            default:
+                k_tsvq_encode<VQB_COSINE><<<grid, 256, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd); break;
+        }
+        VQB_LAUNCHED(ctx);
+        VQB_TRY(lo.finish(ctx));
+        VQB_TRY(ro.finish(ctx));
+        if (!all_dev) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return VQB_SUCCESS;
+}
+
+}  // extern "C"
