@@ -177,6 +177,15 @@ int vqb_pq_encode(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode,
 /* Reconstruction from codes (batch form of pq.rs:193-195 + 201-209): out n*dim f32. */
 int vqb_pq_decode(vqb_pq* pq, const void* codes, uint32_t code_bytes, size_t n, float* out);
 
+/* Diagnostics for the tensor-core assignment kernel (evidence for its error margin):
+ * runs one training-metric (cosine == 0) or cosine-encode (cosine != 0) assignment pass and returns
+ * the raw tcgen05 scores of subspace `sub` (n*256 f32, may be NULL), the number of (row, subspace)
+ * pairs that fell inside the margin and were re-scanned exactly (may be NULL), and the codes
+ * [m][n] u32 (may be NULL).  Not used by any quantizer call. */
+int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, size_t n, size_t dim, size_t m, size_t k,
+                        const float* codebooks, int sub, float* scores_out, uint64_t* rescans_out,
+                        uint32_t* codes_out);
+
 /* ======================= TSVQ ================================================ */
 
 /* TSVQ::new (src/tsvq.rs:195-223) == TSVQNode::build (src/tsvq.rs:31-115), level-synchronous.

@@ -144,5 +144,18 @@ int vqb_pq_assign_exact_launch(vqb_ctx* ctx, int metric_kind, const float* x, si
                                const int* sub_list_dev, int n_sub, void* codes, uint32_t code_bytes,
                                size_t code_stride_row, size_t code_stride_sub, __half* recon);
 
+// tensor-core (tcgen05) GEMM-form assignment, pq_tc.cu.  `prep` is a device workspace of
+// vqb_tc_prep_bytes(m) bytes filled by vqb_tc_prepare from the current codebooks.
+size_t vqb_tc_prep_bytes(size_t m);
+bool vqb_tc_supported(int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k, size_t sub_dim);
+int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t m, size_t k, void* prep);
+int vqb_tc_assign_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k,
+                         const void* prep, const int* active_dev, void* codes, uint32_t code_bytes,
+                         size_t code_stride_row, size_t code_stride_sub, __half* recon,
+                         float* dbg_scores = nullptr, unsigned long long* dbg_stats = nullptr, int dbg_sub = 0);
+// rows below which VQB_ASSIGN_AUTO keeps the CUDA-core kernel (the tensor kernel stages 128 KB of
+// codebooks per CTA before its first tile)
+constexpr size_t VQB_TC_MIN_ROWS = 1024;
+
 // metric_kind for the exact kernel: the four Distance variants + the training distance
 enum { MK_SQEUCLID = 0, MK_EUCLID = 1, MK_MANHATTAN = 2, MK_COSINE = 3, MK_TRAIN = 4 };

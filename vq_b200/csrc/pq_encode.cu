@@ -15,7 +15,9 @@ struct vqb_pq {
     vqb_ctx* ctx = nullptr;
     size_t m = 0, k = 0, d = 0;
     int metric = 0;
-    DevBuf cb;  // [m][k][d] f32
+    DevBuf cb;       // [m][k][d] f32
+    DevBuf tc_prep;  // prepared tensor-core operand images (pq_tc.cu), built once at creation
+    bool tc_ready = false;
 };
 
 namespace {
@@ -44,11 +46,21 @@ struct Event {
 
 int encode_device(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, void* codes, uint32_t code_bytes,
                   __half* recon, cudaStream_t stream_override = nullptr) {
-    (void)assign_mode;
     vqb_ctx* ctx = pq->ctx;
+    const size_t dim = pq->m * pq->d;
+    const bool tc_ok = pq->tc_ready && vqb_tc_supported(pq->metric, x, n, dim, pq->m, pq->k, pq->d);
+    if (assign_mode == VQB_ASSIGN_TENSOR && !tc_ok)
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT,
+                        "tensor-core assignment needs sub_dim 8, k <= 256, a non-Manhattan metric and 16-byte aligned rows");
+    const bool use_tc = tc_ok && (assign_mode == VQB_ASSIGN_TENSOR || (assign_mode == VQB_ASSIGN_AUTO && n >= VQB_TC_MIN_ROWS));
     cudaStream_t saved = ctx->stream;
     if (stream_override) ctx->stream = stream_override;
-    int rc = vqb_pq_assign_exact_launch(ctx, pq->metric, x, n, pq->m * pq->d, pq->m, pq->k, pq->d,
+    int rc;
+    if (use_tc)
+        rc = vqb_tc_assign_launch(ctx, pq->metric, x, n, dim, pq->m, pq->k, pq->tc_prep.p, nullptr, codes, code_bytes,
+                                  /*stride_row=*/pq->m, /*stride_sub=*/1, recon);
+    else
+        rc = vqb_pq_assign_exact_launch(ctx, pq->metric, x, n, pq->m * pq->d, pq->m, pq->k, pq->d,
                                         pq->cb.as<float>(), nullptr, (int)pq->m, codes, code_bytes,
                                         /*stride_row=*/pq->m, /*stride_sub=*/1, recon);
     ctx->stream = saved;
@@ -73,6 +85,11 @@ int vqb_pq_create(vqb_ctx* ctx, const float* codebooks, size_t m, size_t k, size
     size_t bytes = m * k * sub_dim * sizeof(float);
     cudaError_t e = p->cb.alloc(bytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->cb.p, codebooks, bytes, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess && metric != VQB_MANHATTAN && sub_dim == 8 && k <= 256) {
+        e = p->tc_prep.alloc(vqb_tc_prep_bytes(m));
+        if (e == cudaSuccess && vqb_tc_prepare(ctx, metric, p->cb.as<float>(), m, k, p->tc_prep.p) == VQB_SUCCESS)
+            p->tc_ready = true;
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         delete p;

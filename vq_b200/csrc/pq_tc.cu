@@ -1,0 +1,694 @@
+// pq_tc.cu -- GEMM-form nearest-centroid assignment on the 5th-generation tensor cores.
+//
+// Replaces, for sub_dim == 8 and k <= 256, the per-pair distance loops of
+//   find_nearest_centroid      src/core/vector.rs:352-363   (training, squared L2)
+//   ProductQuantizer::quantize src/pq.rs:177-196            (encode: squared L2 / L2 / cosine)
+// by a dense contraction whose result is *decided* with the reference's own arithmetic:
+//
+//   scores  S[row, j] = ||c_j||^2 - 2 x.c_j  (L2 kinds)   or   - x.c_j/||c_j||  (cosine)
+//           = one tcgen05.mma kind::tf32 M=128 N=256 chain per (128-row tile, subspace), K = 4 x 8:
+//             x_hi.c_hi + x_lo.c_hi + x_hi.c_lo (3xTF32 split, ~2^-21 relative) + [1,1,1].[n1,n2,n3]
+//             (the squared norm as three tf32 pieces); accumulators in TMEM (2 x 256 columns).
+//   epilogue one thread per row (= TMEM lane) reads its 256 scores with tcgen05.ld, takes minima
+//           over groups of three columns, and counts -- with saturating FMAs -- the groups that
+//           lie within a rigorous error margin M of the row minimum.  Exactly one such group
+//           (the overwhelmingly common case): its <= 3 centroids are evaluated with the
+//           reference's formula, operation for operation (distance.cuh), and compared with the
+//           reference's strict-'<' / lowest-index rule.  Otherwise (near-ties inside M, NaN/Inf,
+//           degenerate norms) the warp re-scans all k centroids of that row cooperatively, again
+//           with the reference's formula.  Every code is therefore decided by reference
+//           arithmetic; the tensor core only prunes candidates.
+//
+// Decomposition (B-stationary): a CTA owns 4 consecutive subspaces (32 floats = one 128-byte line
+// per row); their prepared codebooks stay in shared memory for the CTA's life and the CTA streams
+// 128-row tiles of its column slab by TMA (SWIZZLE_128B box 32 x 128).  X is read once per pass.
+//
+// Warp roles (448 threads): w0 TMA producer | w1 MMA issuer + TMEM owner | w2-5 hi/lo splitter
+// (fp32 tile -> K-major no-swizzle tf32 operand tiles) | w6-9, w10-13 two epilogue warpgroups, one
+// per TMEM accumulator.  All hand-offs are mbarriers; tcgen05.commit releases smem / signals TMEM.
+#include "common.cuh"
+#include "distance.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+
+namespace {
+
+constexpr int TC_D = 8;            // sub_dim handled here
+constexpr int TC_G = 4;            // subspaces per CTA (4 * 8 floats = 128 B)
+constexpr int TC_N = 256;          // MMA N = centroid slots per subspace
+constexpr int TC_ROWS = 128;       // MMA M = rows per tile = TMEM lanes
+constexpr int RAW_STAGES = 3;
+constexpr int A_STAGES = 3;
+constexpr int TC_THREADS = 448;
+
+constexpr uint32_t RAW_BYTES = TC_ROWS * 128;           // 16 KB per stage
+constexpr uint32_t BP_BYTES = 32 * 6 * 128;             // 24 KB: [32 row groups][6 k-chunks][8 rows][16 B]
+constexpr uint32_t CB_BYTES = TC_N * TC_D * 4;          // 8 KB raw f32 codebook
+constexpr uint32_t AUX_BYTES = TC_N * 8;                // 2 KB (nb, sb) per centroid (cosine)
+constexpr uint32_t AP_BYTES = 16 * 4 * 128;             // 8 KB: [16 row groups][4 k-chunks][8 rows][16 B]
+constexpr uint32_t ONES_BYTES = 16 * 2 * 128;           // 4 KB
+constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES;  // per-subspace prepared image in HBM
+
+constexpr uint32_t OFF_RAW = 0;
+constexpr uint32_t OFF_BP = OFF_RAW + RAW_STAGES * RAW_BYTES;
+constexpr uint32_t OFF_CB = OFF_BP + TC_G * BP_BYTES;
+constexpr uint32_t OFF_AUX = OFF_CB + TC_G * CB_BYTES;
+constexpr uint32_t OFF_AP = OFF_AUX + TC_G * AUX_BYTES;
+constexpr uint32_t OFF_ONES = OFF_AP + A_STAGES * AP_BYTES;
+constexpr uint32_t OFF_BAR = OFF_ONES + ONES_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // barriers + slack for the 1024-byte alignment
+
+template <int D>
+struct RegArr {
+    float v[D];
+    VQB_DEV float operator()(int i) const { return v[i]; }
+};
+
+struct SubInfo {        // per subspace, written by the prepare kernel
+    float cmax2;        // max_j ||c_j||^2 (L2 kinds) ; unused for cosine
+    uint32_t unsafe;    // 1: a centroid component is NaN/Inf or out of range -> every row takes the exact path
+};
+
+// margin constants: M = KAPPA * S, S = (||x|| + max||c||)^2 for the L2 kinds, ||x|| for cosine.
+// Error budget behind it (DESIGN.md "tensor assignment: error bound"): 3xTF32 split 3*2^-22, fp32
+// accumulation of <= 32 products, the norm pieces, and the reference's own rounding (<= 11 ulp of d).
+// Measured on B200 (tests/test_gpu_tensor.py::test_tensor_scores_within_margin): |score - f64| <= 5.3e-7 * S.
+constexpr float KAPPA = 1.0f / 131072.0f;  // 2^-17 = 7.6e-6 >= 2 * (5.3e-7 + 6.6e-7) with 3x to spare
+
+// ------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; LBO = step between the two 16-byte
+// K chunks of one MMA (128 B here), SBO = step between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float to_tf32(float x) {  // round-to-nearest tf32, low 13 bits zero
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float fsat_ind(float g, float negH, float thH) {  // sat((th - g) * H): 1 iff g < th
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(g), "f"(negH), "f"(thH));
+    return r;
+}
+
+// ------------------------------------------------------------------------------- prepare kernel
+// One CTA per subspace, thread j = centroid slot j.  Builds the B operand tile
+// [c_hi | c_lo | norm pieces] in its shared-memory image, a raw f32 copy and the cosine norms.
+template <int MK>
+__global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ codebooks, int k, uint8_t* __restrict__ prep,
+                                                      SubInfo* __restrict__ sinfo) {
+    __shared__ float red[TC_N];
+    __shared__ uint32_t bad;
+    const int s = blockIdx.x, j = threadIdx.x;
+    if (j == 0) bad = 0;
+    __syncthreads();
+    uint8_t* img = prep + (size_t)s * PREP_BYTES;
+    float c[TC_D];
+    const bool real = j < k;
+#pragma unroll
+    for (int i = 0; i < TC_D; ++i) c[i] = real ? codebooks[((size_t)s * k + j) * TC_D + i] : 0.0f;
+    double n2 = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < TC_D; ++i) {
+        n2 += (double)c[i] * (double)c[i];
+        finite = finite && !vqb_bad(c[i]) && fabsf(c[i]) < 1e15f;
+    }
+    if (!finite) atomicOr(&bad, 1u);
+    float b[TC_D];
+    float npiece[3] = {0.f, 0.f, 0.f};
+    if (MK == MK_COSINE) {
+        // scores = -x.c/||c||;  ||c||^2 < FLT_MIN counts as a zero vector (cosine.c:38-45): score 0
+        double inv = (finite && n2 >= (double)FLT_MIN) ? 1.0 / sqrt(n2) : 0.0;
+#pragma unroll
+        for (int i = 0; i < TC_D; ++i) b[i] = finite ? (float)(-(double)c[i] * inv) : 0.0f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < TC_D; ++i) b[i] = finite ? -2.0f * c[i] : 0.0f;
+        double r = finite ? n2 : 0.0;
+        npiece[0] = to_tf32((float)r); r -= (double)npiece[0];
+        npiece[1] = to_tf32((float)r); r -= (double)npiece[1];
+        npiece[2] = to_tf32((float)r);
+    }
+    if (!real) { npiece[0] = 1.0e30f; npiece[1] = npiece[2] = 0.f; }  // padding slots can never be a minimum
+    float hi[TC_D], lo[TC_D];
+#pragma unroll
+    for (int i = 0; i < TC_D; ++i) {
+        hi[i] = to_tf32(b[i]);
+        lo[i] = to_tf32(b[i] - hi[i]);
+    }
+    // B' image: row j, 16-byte k-chunk q at (j/8)*768 + q*128 + (j%8)*16
+    float4* row = reinterpret_cast<float4*>(img + (j >> 3) * 768 + (j & 7) * 16);
+    row[0 * 8] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    row[1 * 8] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+    row[2 * 8] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    row[3 * 8] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    row[4 * 8] = make_float4(npiece[0], npiece[1], npiece[2], 0.f);
+    row[5 * 8] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* raw = reinterpret_cast<float4*>(img + BP_BYTES + j * 32);
+    raw[0] = make_float4(c[0], c[1], c[2], c[3]);
+    raw[1] = make_float4(c[4], c[5], c[6], c[7]);
+    {   // cosine norms exactly as hsd_sim_cosine_f32 accumulates them (cosine.c:163-198)
+        bool tok;
+        RegArr<TC_D> ca;
+#pragma unroll
+        for (int i = 0; i < TC_D; ++i) ca.v[i] = c[i];
+        float nb = hsd_cosine_norm<TC_D>(ca, TC_D, tok);
+        float2* aux = reinterpret_cast<float2*>(img + BP_BYTES + CB_BYTES + j * 8);
+        *aux = make_float2(nb, __fsqrt_rn(nb));
+    }
+    red[j] = (real && finite) ? (float)n2 : 0.0f;
+    __syncthreads();
+    for (int st = TC_N / 2; st > 0; st >>= 1) {
+        if (j < st) red[j] = fmaxf(red[j], red[j + st]);
+        __syncthreads();
+    }
+    if (j == 0) {
+        SubInfo si;
+        si.cmax2 = red[0] * 1.0000005f;
+        si.unsafe = bad;
+        sinfo[s] = si;
+    }
+}
+
+// ---------------------------------------------------------------------------- exact evaluation
+// The reference's distance between the row's sub-vector (registers) and centroid j (shared memory).
+template <int MK>
+struct ExactEval {
+    RegArr<TC_D> x;
+    float na, sa;
+    bool a_tail_ok;
+    __device__ __forceinline__ void init() {
+        na = sa = 0.f; a_tail_ok = true;
+        if (MK == MK_COSINE) { na = hsd_cosine_norm<TC_D>(x, TC_D, a_tail_ok); sa = __fsqrt_rn(na); }
+    }
+    __device__ __forceinline__ float operator()(const float* cb, const float2* aux, int j) const {
+        PtrAcc cp{cb + j * TC_D};
+        if (MK == MK_TRAIN) return dist2_seq<TC_D>(x, cp, TC_D);
+        if (MK == MK_COSINE) {
+            float dot = hsd_cosine_dot<TC_D>(x, cp, TC_D);
+            float2 a = aux[j];
+            bool ok = a_tail_ok;  // codebook components are finite here (else the subspace is `unsafe`)
+            float sim = 0.f;
+            if (ok) sim = hsd_cosine_from_sums(dot, na, a.x, sa, a.y, ok);
+            return ok ? __fsub_rn(1.0f, sim) : rust_cos<TC_D>(x, cp, TC_D);
+        }
+        return vq_distance<TC_D>(MK, x, cp, TC_D);
+    }
+};
+
+struct TcParams {
+    const uint8_t* prep;        // [m] prepared images
+    const SubInfo* sinfo;       // [m]
+    const int* active;          // [m] 0/1 or nullptr (all active)
+    void* codes;
+    __half* recon;
+    unsigned long long n;
+    unsigned long long stride_row, stride_sub;
+    int dim, m, k, n_groups, parts, num_tiles;
+    uint32_t code_bytes;
+    float* dbg_scores;            // DEBUG kernels only: [n][256] raw tensor-core scores of subspace dbg_sub
+    unsigned long long* dbg_stats;  // DEBUG kernels only: [0] (row, subspace) pairs resolved by the full re-scan
+    int dbg_sub;
+};
+
+__device__ __forceinline__ void store_code(void* codes, uint32_t code_bytes, size_t off, uint32_t v) {
+    if (code_bytes == 1) static_cast<uint8_t*>(codes)[off] = (uint8_t)v;
+    else if (code_bytes == 2) static_cast<uint16_t*>(codes)[off] = (uint16_t)v;
+    else static_cast<uint32_t*>(codes)[off] = v;
+}
+
+// ----------------------------------------------------------------------------------- main kernel
+template <int MK, bool DEBUG>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.x % p.n_groups, part = blockIdx.x / p.n_groups;
+    const int s0 = grp * TC_G;
+    const int g_cnt = min(TC_G, p.m - s0);
+
+    // barriers
+    const uint32_t bar0 = sbase + OFF_BAR;
+    auto RAW_FULL = [&](int i) { return bar0 + 8u * i; };
+    auto RAW_EMPTY = [&](int i) { return bar0 + 8u * (RAW_STAGES + i); };
+    auto A_FULL = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + i); };
+    auto A_EMPTY = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + A_STAGES + i); };
+    auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + 2 * A_STAGES + i); };
+    auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + 2 * A_STAGES + 2 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8 * (2 * RAW_STAGES + 2 * A_STAGES + 4));
+
+    // active subspaces of this group (same list for every role)
+    uint32_t act_mask = 0;
+    for (int i = 0; i < g_cnt; ++i)
+        if (!p.active || p.active[s0 + i]) act_mask |= 1u << i;
+    const int n_act = __popc(act_mask);
+    if (n_act == 0) return;
+
+    // ---- one-time setup: prepared codebooks -> smem, constant ones tile, barriers, TMEM
+    for (int i = 0; i < TC_G; ++i) {
+        const int s = min(s0 + i, p.m - 1);
+        const float4* src = reinterpret_cast<const float4*>(p.prep + (size_t)s * PREP_BYTES);
+        float4* dbp = reinterpret_cast<float4*>(sm + OFF_BP + i * BP_BYTES);
+        float4* dcb = reinterpret_cast<float4*>(sm + OFF_CB + i * CB_BYTES);
+        float4* dax = reinterpret_cast<float4*>(sm + OFF_AUX + i * AUX_BYTES);
+        for (int t = threadIdx.x; t < (int)(BP_BYTES / 16); t += TC_THREADS) dbp[t] = __ldg(src + t);
+        for (int t = threadIdx.x; t < (int)(CB_BYTES / 16); t += TC_THREADS) dcb[t] = __ldg(src + BP_BYTES / 16 + t);
+        for (int t = threadIdx.x; t < (int)(AUX_BYTES / 16); t += TC_THREADS) dax[t] = __ldg(src + (BP_BYTES + CB_BYTES) / 16 + t);
+    }
+    for (int t = threadIdx.x; t < (int)(ONES_BYTES / 16); t += TC_THREADS) {
+        // [16 groups][2 chunks][8 rows][16 B]: chunk 0 = (1,1,1,0), chunk 1 = 0
+        const bool chunk0 = ((t >> 3) & 1) == 0;
+        reinterpret_cast<float4*>(sm + OFF_ONES)[t] = chunk0 ? make_float4(1.f, 1.f, 1.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(RAW_FULL(i), 1); mbar_init(RAW_EMPTY(i), 128 + 128 * n_act); }
+        for (int i = 0; i < A_STAGES; ++i) { mbar_init(A_FULL(i), 128); mbar_init(A_EMPTY(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();  // generic-proxy smem writes above -> visible to the tensor core / TMA
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int my_tiles = (p.num_tiles - part + p.parts - 1) / p.parts;  // tiles part, part+parts, ...
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            for (int it = 0; it < my_tiles; ++it) {
+                const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
+                mbar_wait(RAW_EMPTY(st), ph ^ 1);
+                mbar_expect_tx(RAW_FULL(st), RAW_BYTES);
+                const int tile = part + it * p.parts;
+                tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+            const uint64_t ones_desc = make_desc(sbase + OFF_ONES, 128, 256);
+            const bool use_norm = (MK != MK_COSINE) || (p.k < TC_N);
+            uint32_t u = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int i = 0; i < g_cnt; ++i) {
+                    if (!(act_mask >> i & 1)) continue;
+                    const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
+                    const int acc = u & 1, cph = (u >> 1) & 1;
+                    mbar_wait(A_FULL(ast), aph);
+                    mbar_wait(ACC_EMPTY(acc), cph ^ 1);
+                    tc_fence_after();
+                    const uint32_t a0 = sbase + OFF_AP + ast * AP_BYTES, b0 = sbase + OFF_BP + i * BP_BYTES;
+                    const uint32_t d = tmem_base + acc * TC_N;
+                    umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0, 128, 768), idesc, 0);              // x_hi . c_hi
+                    umma_tf32(d, make_desc(a0 + 256, 128, 512), make_desc(b0, 128, 768), idesc, 1);        // x_lo . c_hi
+                    umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0 + 256, 128, 768), idesc, 1);        // x_hi . c_lo
+                    if (use_norm) umma_tf32(d, ones_desc, make_desc(b0 + 512, 128, 768), idesc, 1);        // + ||c||^2
+                    umma_commit(A_EMPTY(ast));
+                    umma_commit(ACC_FULL(acc));
+                    ++u;
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ================================ hi/lo splitter ==============================
+        const int r = (warp - 2) * 32 + lane;  // tile row
+        uint32_t u = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
+            mbar_wait(RAW_FULL(st), ph);
+            const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
+            for (int i = 0; i < g_cnt; ++i) {
+                if (!(act_mask >> i & 1)) continue;
+                const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
+                // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+                const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
+                const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
+                float4 h0, h1, l0, l1;
+                h0.x = to_tf32(v0.x); h0.y = to_tf32(v0.y); h0.z = to_tf32(v0.z); h0.w = to_tf32(v0.w);
+                h1.x = to_tf32(v1.x); h1.y = to_tf32(v1.y); h1.z = to_tf32(v1.z); h1.w = to_tf32(v1.w);
+                l0.x = to_tf32(v0.x - h0.x); l0.y = to_tf32(v0.y - h0.y); l0.z = to_tf32(v0.z - h0.z); l0.w = to_tf32(v0.w - h0.w);
+                l1.x = to_tf32(v1.x - h1.x); l1.y = to_tf32(v1.y - h1.y); l1.z = to_tf32(v1.z - h1.z); l1.w = to_tf32(v1.w - h1.w);
+                mbar_wait(A_EMPTY(ast), aph ^ 1);
+                float4* dst = reinterpret_cast<float4*>(sm + OFF_AP + ast * AP_BYTES + (r >> 3) * 512 + (r & 7) * 16);
+                dst[0 * 8] = h0; dst[1 * 8] = h1; dst[2 * 8] = l0; dst[3 * 8] = l1;
+                fence_proxy_async();
+                mbar_arrive(A_FULL(ast));
+                ++u;
+            }
+            mbar_arrive(RAW_EMPTY(st));
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const int wg = (warp - 6) >> 2;             // warpgroup = TMEM accumulator
+        const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+        const int r = quarter * 32 + lane;          // tile row = TMEM lane
+        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        uint32_t u = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
+            const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
+            const bool live = row < p.n;
+            bool raw_seen = false;
+            for (int i = 0; i < g_cnt; ++i) {
+                if (!(act_mask >> i & 1)) continue;
+                if ((int)(u & 1) != wg) { ++u; continue; }
+                const int cph = (u >> 1) & 1;
+                ++u;
+                const int s = s0 + i;
+                if (!raw_seen) { mbar_wait(RAW_FULL(st), ph); raw_seen = true; }
+                // this row's sub-vector, margin and flags
+                ExactEval<MK> ev;
+                {
+                    const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
+                    const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
+                    ev.x.v[0] = v0.x; ev.x.v[1] = v0.y; ev.x.v[2] = v0.z; ev.x.v[3] = v0.w;
+                    ev.x.v[4] = v1.x; ev.x.v[5] = v1.y; ev.x.v[6] = v1.z; ev.x.v[7] = v1.w;
+                }
+                ev.init();
+                float nx2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < TC_D; ++q) nx2 = fmaf(ev.x.v[q], ev.x.v[q], nx2);
+                const SubInfo si = p.sinfo[s];
+                float S;
+                if (MK == MK_COSINE) S = sqrtf(nx2);
+                else { float t = sqrtf(nx2) + sqrtf(si.cmax2); S = t * t; }
+                const float M = KAPPA * S;
+                // rows the pruning cannot be trusted on: NaN/Inf/huge/tiny magnitudes, hsdlib zero rule
+                bool amb = si.unsafe || !(nx2 < 1e30f) || !(S > 1e-25f) || !(S < 1e30f);
+                if (MK == MK_COSINE) amb = amb || !(ev.na >= FLT_MIN) || !ev.a_tail_ok;
+                // indicator scale H = 2^(40 - floor(log2 S)): (th - g) * H >= 1 for every representable g < th
+                // in the score range, and th * H stays far from overflow
+                const uint32_t sexp = (__float_as_uint(S) >> 23) & 0xFFu;
+                const float H = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
+                const float negH = -H, MH = M * H;
+
+                mbar_wait(ACC_FULL(wg), cph);
+                tc_fence_after();
+                float cm[8], ac[8];
+                const uint32_t tcol = tmem_base + tlane + wg * TC_N;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tcol + c * 32, v);
+                    tmem_ld_wait();
+                    if (DEBUG && p.dbg_scores && s == p.dbg_sub && live) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) p.dbg_scores[(size_t)row * TC_N + c * 32 + q] = __uint_as_float(v[q]);
+                    }
+                    float g[11];
+#pragma unroll
+                    for (int t = 0; t < 10; ++t)
+                        g[t] = fminf(fminf(__uint_as_float(v[3 * t]), __uint_as_float(v[3 * t + 1])), __uint_as_float(v[3 * t + 2]));
+                    g[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+                    const float m0 = fminf(fminf(g[0], g[1]), g[2]), m1 = fminf(fminf(g[3], g[4]), g[5]);
+                    const float m2 = fminf(fminf(g[6], g[7]), g[8]), m3 = fminf(g[9], g[10]);
+                    const float mc = fminf(fminf(fminf(m0, m1), m2), m3);
+                    const float thH = fmaf(mc, H, MH);  // (mc + M) * H
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 11; ++t) {
+                        const float w = (float)(32 + t), ind = fsat_ind(g[t], negH, thH);
+                        if ((t & 3) == 0) a0 = fmaf(ind, w, a0);
+                        if ((t & 3) == 1) a1 = fmaf(ind, w, a1);
+                        if ((t & 3) == 2) a2 = fmaf(ind, w, a2);
+                        if ((t & 3) == 3) a3 = fmaf(ind, w, a3);
+                    }
+                    cm[c] = mc;
+                    ac[c] = (a0 + a1) + (a2 + a3);
+                }
+                tc_fence_before();
+                mbar_arrive(ACC_EMPTY(wg));  // TMEM accumulator may be overwritten by the next MMA chain
+
+                // ---- resolve: exactly one chunk and one group inside the margin?
+                float mall = cm[0];
+#pragma unroll
+                for (int c = 1; c < 8; ++c) mall = fminf(mall, cm[c]);
+                const float thr = mall + M;
+                int nfl = 0, wsel = 0;
+                float accw = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const bool f = cm[c] < thr;
+                    nfl += f ? 1 : 0;
+                    if (f) { wsel = c; accw = ac[c]; }
+                }
+                const bool single = (nfl == 1) && (accw >= 32.f) && (accw <= 42.f) && (accw == floorf(accw));
+                amb = amb || !single;
+                const float* cb = reinterpret_cast<const float*>(sm + OFF_CB + i * CB_BYTES);
+                const float2* aux = reinterpret_cast<const float2*>(sm + OFF_AUX + i * AUX_BYTES);
+                uint32_t best = 0;
+                if (!amb) {
+                    const int t = (int)accw - 32;
+                    const int j0 = wsel * 32 + 3 * t;
+                    best = (uint32_t)j0;
+                    float bd = ev(cb, aux, j0);
+#pragma unroll
+                    for (int q = 1; q < 3; ++q) {
+                        const int j = j0 + q;
+                        if (j < p.k && !(t == 10 && q == 2)) {
+                            const float dd = ev(cb, aux, j);
+                            if (dd < bd) { bd = dd; best = (uint32_t)j; }
+                        }
+                    }
+                }
+                // ---- rows inside the margin: the warp scans all k centroids with the reference formula
+                uint32_t todo = __ballot_sync(0xFFFFFFFFu, amb && live);
+                if (DEBUG && p.dbg_stats && lane == 0 && todo) atomicAdd(p.dbg_stats, (unsigned long long)__popc(todo));
+                while (todo) {
+                    const int L = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    ExactEval<MK> eo;
+#pragma unroll
+                    for (int q = 0; q < TC_D; ++q) eo.x.v[q] = __shfl_sync(0xFFFFFFFFu, ev.x.v[q], L);
+                    eo.init();
+                    float bd = __int_as_float(0x7f800000);
+                    uint32_t bj = 0xFFFFFFFFu;
+                    bool d0nan = false;
+                    for (int j = lane; j < p.k; j += 32) {
+                        float dd = eo(cb, aux, j);
+                        if (j == 0) d0nan = isnan(dd);
+                        if (isnan(dd)) dd = __int_as_float(0x7f800000);
+                        if (bj == 0xFFFFFFFFu || dd < bd) { bd = dd; bj = (uint32_t)j; }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float od = __shfl_xor_sync(0xFFFFFFFFu, bd, off);
+                        const uint32_t oj = __shfl_xor_sync(0xFFFFFFFFu, bj, off);
+                        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                    }
+                    d0nan = __shfl_sync(0xFFFFFFFFu, d0nan ? 1 : 0, 0) != 0;
+                    if (lane == L) best = d0nan ? 0u : bj;  // vector.rs:354-361: a NaN at index 0 is never replaced
+                }
+                if (live) {
+                    if (p.codes) store_code(p.codes, p.code_bytes, (size_t)row * p.stride_row + (size_t)s * p.stride_sub, best);
+                    if (p.recon) {  // pq.rs:193-195: f16::from_f32 of the chosen centroid
+                        const float* c = cb + best * TC_D;
+                        __half2 h[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(c[2 * q], c[2 * q + 1]);
+                        *reinterpret_cast<uint4*>(p.recon + (size_t)row * p.dim + (size_t)s * TC_D) = *reinterpret_cast<uint4*>(h);
+                    }
+                }
+                mbar_arrive(RAW_EMPTY(st));
+            }
+            // units of this tile that belong to the other warpgroup still count one arrival each there
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(f);
+    });
+    return fn;
+}
+
+template <int MK, bool DEBUG = false>
+int launch_tc(vqb_ctx* ctx, const CUtensorMap& map, const TcParams& p, int grid) {
+    auto kern = k_tc_assign<MK, DEBUG>;
+    VQB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    kern<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(map, p);
+    VQB_LAUNCHED(ctx);
+    return VQB_SUCCESS;
+}
+
+}  // namespace
+
+size_t vqb_tc_prep_bytes(size_t m) { return m * (size_t)PREP_BYTES + m * sizeof(SubInfo) + 256; }
+
+bool vqb_tc_supported(int mk, const float* x, size_t n, size_t dim, size_t m, size_t k, size_t d) {
+    (void)m;
+    if (mk == MK_MANHATTAN) return false;                 // not a contraction: CUDA-core kernel by design
+    if (d != TC_D || k == 0 || k > TC_N) return false;
+    if (dim % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return false;  // TMA: 16-byte aligned rows
+    if (n == 0 || n >= (size_t)1 << 31) return false;
+    return get_encode_fn() != nullptr;
+}
+
+int vqb_tc_prepare(vqb_ctx* ctx, int mk, const float* codebooks, size_t m, size_t k, void* prep) {
+    uint8_t* img = static_cast<uint8_t*>(prep);
+    SubInfo* sinfo = reinterpret_cast<SubInfo*>(img + ((m * (size_t)PREP_BYTES + 255) & ~(size_t)255));
+    if (mk == MK_COSINE) k_tc_prepare<MK_COSINE><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo);
+    else k_tc_prepare<MK_TRAIN><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo);
+    VQB_LAUNCHED(ctx);
+    return VQB_SUCCESS;
+}
+
+int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t dim, size_t m, size_t k, const void* prep,
+                         const int* active_dev, void* codes, uint32_t code_bytes, size_t stride_row, size_t stride_sub,
+                         __half* recon, float* dbg_scores, unsigned long long* dbg_stats, int dbg_sub) {
+    if (n == 0) return VQB_SUCCESS;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled is not available");
+    CUtensorMap map;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    TcParams p;
+    const uint8_t* img = static_cast<const uint8_t*>(prep);
+    p.prep = img;
+    p.sinfo = reinterpret_cast<const SubInfo*>(img + ((m * (size_t)PREP_BYTES + 255) & ~(size_t)255));
+    p.active = active_dev;
+    p.codes = codes; p.recon = recon;
+    p.n = n; p.stride_row = stride_row; p.stride_sub = stride_sub;
+    p.dim = (int)dim; p.m = (int)m; p.k = (int)k;
+    p.n_groups = (int)((m + TC_G - 1) / TC_G);
+    p.num_tiles = (int)((n + TC_ROWS - 1) / TC_ROWS);
+    p.parts = std::max(1, std::min(p.num_tiles, ctx->sm_count / p.n_groups));
+    p.code_bytes = code_bytes;
+    p.dbg_scores = dbg_scores; p.dbg_stats = dbg_stats; p.dbg_sub = dbg_sub;
+    const int grid = p.n_groups * p.parts;
+    if (dbg_scores || dbg_stats) {
+        if (mk == MK_COSINE) return launch_tc<MK_COSINE, true>(ctx, map, p, grid);
+        if (mk == MK_TRAIN) return launch_tc<MK_TRAIN, true>(ctx, map, p, grid);
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for the training and cosine kinds only");
+    }
+    switch (mk) {
+        case MK_SQEUCLID: return launch_tc<MK_SQEUCLID>(ctx, map, p, grid);
+        case MK_EUCLID: return launch_tc<MK_EUCLID>(ctx, map, p, grid);
+        case MK_COSINE: return launch_tc<MK_COSINE>(ctx, map, p, grid);
+        case MK_TRAIN: return launch_tc<MK_TRAIN>(ctx, map, p, grid);
+    }
+    return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "metric kind %d has no tensor-core path", mk);
+}
+
+extern "C" int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, size_t n, size_t dim, size_t m, size_t k,
+                                   const float* codebooks, int sub, float* scores_out, uint64_t* rescans_out,
+                                   uint32_t* codes_out) {
+    if (!ctx || !x || !codebooks) return VQB_ERR_NULL_PTR;
+    if (m == 0 || dim % m) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "dim must be divisible by m");
+    const size_t d = dim / m;
+    const int mk = cosine ? MK_COSINE : MK_TRAIN;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    InputView xin, cin;
+    OutputView so, co;
+    VQB_TRY(xin.bind(ctx, x, n * dim * 4));
+    VQB_TRY(cin.bind(ctx, codebooks, m * k * d * 4));
+    VQB_TRY(so.bind(ctx, scores_out, scores_out ? n * TC_N * 4 : 0));
+    VQB_TRY(co.bind(ctx, codes_out, codes_out ? m * n * 4 : 0));
+    if (!vqb_tc_supported(mk, static_cast<const float*>(xin.dev), n, dim, m, k, d))
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "shape not covered by the tensor-core kernel");
+    DevBuf prep, stats;
+    VQB_CUDA(ctx, prep.alloc(vqb_tc_prep_bytes(m)));
+    VQB_CUDA(ctx, stats.alloc(8));
+    VQB_CUDA(ctx, cudaMemsetAsync(stats.p, 0, 8, ctx->stream));
+    VQB_TRY(vqb_tc_prepare(ctx, mk, static_cast<const float*>(cin.dev), m, k, prep.p));
+    VQB_TRY(vqb_tc_assign_launch(ctx, mk, static_cast<const float*>(xin.dev), n, dim, m, k, prep.p, nullptr, co.dev, 4,
+                                 /*stride_row=*/1, /*stride_sub=*/n, nullptr, static_cast<float*>(so.dev),
+                                 stats.as<unsigned long long>(), sub));
+    VQB_TRY(so.finish(ctx));
+    VQB_TRY(co.finish(ctx));
+    if (rescans_out) VQB_CUDA(ctx, cudaMemcpyAsync(rescans_out, stats.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VQB_SUCCESS;
+}

@@ -244,7 +244,7 @@ struct TrainWs {
     uint32_t code_bytes = 1;
     int n_chunks = 0, segs = 1, passes = 1;
     DevBuf codes, ids_a, ids_b, chunk_hist, bin_off, seg_beg, seg_end, partial, pack, cb;
-    DevBuf sub_list, is_active, changed, counts, g_rows, g_subs, g_dst, g_vals;
+    DevBuf sub_list, is_active, changed, counts, g_rows, g_subs, g_dst, g_vals, tc_prep;
     int alloc(vqb_ctx* ctx, size_t n_, size_t dim_, size_t m_, size_t k_, int segs_) {
         n = n_; dim = dim_; m = m_; k = k_; d = dim / m; segs = segs_;
         code_bytes = k <= 256 ? 1 : (k <= 65536 ? 2 : 4);
@@ -269,6 +269,7 @@ struct TrainWs {
         VQB_CUDA(ctx, g_subs.alloc(gcap * 4));
         VQB_CUDA(ctx, g_dst.alloc(gcap * 8));
         VQB_CUDA(ctx, g_vals.alloc(gcap * d * 4));
+        VQB_CUDA(ctx, tc_prep.alloc(vqb_tc_prep_bytes(m)));
         return VQB_SUCCESS;
     }
 };
@@ -280,9 +281,20 @@ struct TrainArgs {
     uint64_t row_offset;
 };
 
-int assign_train(vqb_ctx* ctx, const TrainArgs& a, const float* cb, const int* sub_list, int na, void* codes,
-                 uint32_t code_bytes) {
+// `is_active` (device, [m] 0/1, may be null = all) and `sub_list` (device, the same set as a list, may be
+// null = all) describe the subspaces to assign; `tc_prep` is the tensor-core workspace (may be null).
+int assign_train(vqb_ctx* ctx, const TrainArgs& a, const float* cb, const int* sub_list, const int* is_active, int na,
+                 void* codes, uint32_t code_bytes, void* tc_prep) {
     // codes[s*n + row]
+    const bool tc_ok = tc_prep && vqb_tc_supported(MK_TRAIN, a.x, a.n, a.dim, a.m, a.k, a.d);
+    if (a.assign_mode == VQB_ASSIGN_TENSOR && !tc_ok)
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT,
+                        "tensor-core assignment needs sub_dim 8, k <= 256 and 16-byte aligned rows");
+    if (tc_ok && (a.assign_mode == VQB_ASSIGN_TENSOR || (a.assign_mode == VQB_ASSIGN_AUTO && a.n >= VQB_TC_MIN_ROWS))) {
+        VQB_TRY(vqb_tc_prepare(ctx, MK_TRAIN, cb, a.m, a.k, tc_prep));
+        return vqb_tc_assign_launch(ctx, MK_TRAIN, a.x, a.n, a.dim, a.m, a.k, tc_prep, is_active, codes, code_bytes,
+                                    /*stride_row=*/1, /*stride_sub=*/a.n, nullptr);
+    }
     return vqb_pq_assign_exact_launch(ctx, MK_TRAIN, a.x, a.n, a.dim, a.m, a.k, a.d, cb, sub_list, na, codes,
                                       code_bytes, /*stride_row=*/1, /*stride_sub=*/a.n, nullptr);
 }
@@ -315,7 +327,8 @@ int train_iteration(vqb_ctx* ctx, TrainWs& ws, const TrainArgs& a, const std::ve
     VQB_CUDA(ctx, cudaMemsetAsync(ws.changed.p, 0, m * 4, ctx->stream));
     const int* sl = ws.sub_list.as<int>();
 
-    VQB_TRY(assign_train(ctx, a, ws.cb.as<float>(), sl, na, ws.codes.p, ws.code_bytes));
+    VQB_TRY(assign_train(ctx, a, ws.cb.as<float>(), sl, ws.is_active.as<int>(), na, ws.codes.p, ws.code_bytes,
+                         ws.tc_prep.p));
 
     // group: LSD radix, 8 bits per stable pass
     const uint32_t* ids_in = nullptr;
@@ -510,7 +523,9 @@ int vqb_pq_assign_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size
     VQB_TRY(cin.bind(ctx, codebooks, m * k * d * 4));
     VQB_TRY(ov.bind(ctx, codes_out, m * n * 4));
     TrainArgs a{static_cast<const float*>(xin.dev), n, dim, m, k, d, assign_mode, nullptr, nullptr, 0};
-    VQB_TRY(assign_train(ctx, a, static_cast<const float*>(cin.dev), nullptr, (int)m, ov.dev, 4));
+    DevBuf tcp;
+    VQB_CUDA(ctx, tcp.alloc(vqb_tc_prep_bytes(m)));
+    VQB_TRY(assign_train(ctx, a, static_cast<const float*>(cin.dev), nullptr, nullptr, (int)m, ov.dev, 4, tcp.p));
     VQB_TRY(ov.finish(ctx));
     VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VQB_SUCCESS;
