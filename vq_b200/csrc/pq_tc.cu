@@ -23,9 +23,17 @@
 // per row); their prepared codebooks stay in shared memory for the CTA's life and the CTA streams
 // 128-row tiles of its column slab by TMA (SWIZZLE_128B box 32 x 128).  X is read once per pass.
 //
-// Warp roles (448 threads): w0 TMA producer | w1 MMA issuer + TMEM owner | w2-5 hi/lo splitter
-// (fp32 tile -> K-major no-swizzle tf32 operand tiles) | w6-9, w10-13 two epilogue warpgroups, one
-// per TMEM accumulator.  All hand-offs are mbarriers; tcgen05.commit releases smem / signals TMEM.
+// Warp roles (768 threads = 6 warpgroups, registers re-balanced with setmaxnreg):
+//   WG0  w0 TMA producer | w1 MMA issuer + TMEM owner | w2-3 idle
+//   WG1  hi/lo splitter: fp32 tile -> K-major no-swizzle tf32 operand tiles, + the row's error margin
+//   WG2-3 scan: one warpgroup per TMEM accumulator; thread = row = TMEM lane; pure register work
+//         (tcgen05.ld, FMNMX3 minima, saturating-FMA indicators) -> one candidate group or "ambiguous"
+//   WG4-5 resolve: reference-arithmetic evaluation of the candidate group (or the full re-scan),
+//         code / f16 reconstruction stores
+// The per-unit chain split -> MMA -> scan -> resolve is a software pipeline over shared-memory rings;
+// all hand-offs are mbarriers; tcgen05.commit releases smem / signals TMEM.  Splitting the old
+// single epilogue role in two keeps ~5 warps per SM sub-partition busy instead of 2 (the v1 kernel
+// issued on 43 % of cycles with its epilogue warps stalled on their own dependency chains).
 #include "common.cuh"
 #include "distance.cuh"
 
@@ -41,7 +49,14 @@ constexpr int TC_N = 256;          // MMA N = centroid slots per subspace
 constexpr int TC_ROWS = 128;       // MMA M = rows per tile = TMEM lanes
 constexpr int RAW_STAGES = 3;
 constexpr int A_STAGES = 3;
-constexpr int TC_THREADS = 448;
+constexpr int MG_STAGES = 4;       // splitter -> scan: per-row margin
+constexpr int RES_STAGES = 4;      // scan -> resolve: per-row candidate
+constexpr int TC_THREADS = 768;
+// setmaxnreg budget: the pool is what the CTA was launched with (768 threads x 80 registers = 61440), so
+// 128*24 + 128*48 + 256*128 + 256*72 = 60416 must not exceed it or the last setmaxnreg.inc never returns
+constexpr int REGS_LAUNCH = 80, REGS_CTRL = 24, REGS_SPLIT = 48, REGS_SCAN = 128, REGS_RESOLVE = 72;
+static_assert(128 * REGS_CTRL + 128 * REGS_SPLIT + 256 * REGS_SCAN + 256 * REGS_RESOLVE <= TC_THREADS * REGS_LAUNCH,
+              "setmaxnreg budget exceeds the registers the CTA owns");
 
 constexpr uint32_t RAW_BYTES = TC_ROWS * 128;           // 16 KB per stage
 constexpr uint32_t BP_BYTES = 32 * 6 * 128;             // 24 KB: [32 row groups][6 k-chunks][8 rows][16 B]
@@ -49,6 +64,8 @@ constexpr uint32_t CB_BYTES = TC_N * TC_D * 4;          // 8 KB raw f32 codebook
 constexpr uint32_t AUX_BYTES = TC_N * 8;                // 2 KB (nb, sb) per centroid (cosine)
 constexpr uint32_t AP_BYTES = 16 * 4 * 128;             // 8 KB: [16 row groups][4 k-chunks][8 rows][16 B]
 constexpr uint32_t ONES_BYTES = 16 * 2 * 128;           // 4 KB
+constexpr uint32_t MG_BYTES = TC_ROWS * 8;              // float2 {H, M} per row
+constexpr uint32_t RES_BYTES = TC_ROWS * 4;             // u32 candidate per row
 constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES;  // per-subspace prepared image in HBM
 
 constexpr uint32_t OFF_RAW = 0;
@@ -57,8 +74,13 @@ constexpr uint32_t OFF_CB = OFF_BP + TC_G * BP_BYTES;
 constexpr uint32_t OFF_AUX = OFF_CB + TC_G * CB_BYTES;
 constexpr uint32_t OFF_AP = OFF_AUX + TC_G * AUX_BYTES;
 constexpr uint32_t OFF_ONES = OFF_AP + A_STAGES * AP_BYTES;
-constexpr uint32_t OFF_BAR = OFF_ONES + ONES_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // barriers + slack for the 1024-byte alignment
+constexpr uint32_t OFF_MG = OFF_ONES + ONES_BYTES;
+constexpr uint32_t OFF_RES = OFF_MG + MG_STAGES * MG_BYTES;
+constexpr uint32_t OFF_SINFO = OFF_RES + RES_STAGES * RES_BYTES;  // TC_G x {sqrt(cmax2), unsafe}
+constexpr uint32_t OFF_BAR = OFF_SINFO + 64;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // barriers + slack for the 1024-byte alignment
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+constexpr uint32_t RES_AMBIGUOUS = 0xFFFFFFFFu;
 
 template <int D>
 struct RegArr {
@@ -87,10 +109,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!ok) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x4000u)  // suspend-time hint (ns): waiters sleep in hardware, not in the issue slots
             : "memory");
     }
 }
@@ -147,6 +169,13 @@ __device__ __forceinline__ float to_tf32(float x) {  // round-to-nearest tf32, l
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 __device__ __forceinline__ float fsat_ind(float g, float negH, float thH) {  // sat((th - g) * H): 1 iff g < th
     float r;
@@ -288,19 +317,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wgrp = warp >> 2;
     const int grp = blockIdx.x % p.n_groups, part = blockIdx.x / p.n_groups;
     const int s0 = grp * TC_G;
     const int g_cnt = min(TC_G, p.m - s0);
 
     // barriers
     const uint32_t bar0 = sbase + OFF_BAR;
+    constexpr int B_RAW_EMPTY = RAW_STAGES, B_A_FULL = 2 * RAW_STAGES, B_A_EMPTY = B_A_FULL + A_STAGES;
+    constexpr int B_ACC_FULL = B_A_EMPTY + A_STAGES, B_ACC_EMPTY = B_ACC_FULL + 2;
+    constexpr int B_MG_FULL = B_ACC_EMPTY + 2, B_MG_EMPTY = B_MG_FULL + MG_STAGES;
+    constexpr int B_RES_FULL = B_MG_EMPTY + MG_STAGES, B_RES_EMPTY = B_RES_FULL + RES_STAGES;
+    constexpr int B_COUNT = B_RES_EMPTY + RES_STAGES;
+    static_assert(B_COUNT * 8 + 8 <= 512, "barrier area too small");
     auto RAW_FULL = [&](int i) { return bar0 + 8u * i; };
-    auto RAW_EMPTY = [&](int i) { return bar0 + 8u * (RAW_STAGES + i); };
-    auto A_FULL = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + i); };
-    auto A_EMPTY = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + A_STAGES + i); };
-    auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + 2 * A_STAGES + i); };
-    auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * RAW_STAGES + 2 * A_STAGES + 2 + i); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8 * (2 * RAW_STAGES + 2 * A_STAGES + 4));
+    auto RAW_EMPTY = [&](int i) { return bar0 + 8u * (B_RAW_EMPTY + i); };
+    auto A_FULL = [&](int i) { return bar0 + 8u * (B_A_FULL + i); };
+    auto A_EMPTY = [&](int i) { return bar0 + 8u * (B_A_EMPTY + i); };
+    auto ACC_FULL = [&](int i) { return bar0 + 8u * (B_ACC_FULL + i); };
+    auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (B_ACC_EMPTY + i); };
+    auto MG_FULL = [&](int i) { return bar0 + 8u * (B_MG_FULL + i); };
+    auto MG_EMPTY = [&](int i) { return bar0 + 8u * (B_MG_EMPTY + i); };
+    auto RES_FULL = [&](int i) { return bar0 + 8u * (B_RES_FULL + i); };
+    auto RES_EMPTY = [&](int i) { return bar0 + 8u * (B_RES_EMPTY + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8 * B_COUNT);
 
     // active subspaces of this group (same list for every role)
     uint32_t act_mask = 0;
@@ -325,10 +365,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         const bool chunk0 = ((t >> 3) & 1) == 0;
         reinterpret_cast<float4*>(sm + OFF_ONES)[t] = chunk0 ? make_float4(1.f, 1.f, 1.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (threadIdx.x < TC_G) {  // per-subspace margin inputs: {sqrt(max ||c||^2), unsafe}
+        const SubInfo si = p.sinfo[min(s0 + (int)threadIdx.x, p.m - 1)];
+        reinterpret_cast<float2*>(sm + OFF_SINFO)[threadIdx.x] = make_float2(sqrtf(si.cmax2) * 1.0000005f, si.unsafe ? 1.0f : 0.0f);
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(RAW_FULL(i), 1); mbar_init(RAW_EMPTY(i), 128 + 128 * n_act); }
         for (int i = 0; i < A_STAGES; ++i) { mbar_init(A_FULL(i), 128); mbar_init(A_EMPTY(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 128); }
+        for (int i = 0; i < MG_STAGES; ++i) { mbar_init(MG_FULL(i), 128); mbar_init(MG_EMPTY(i), 128); }
+        for (int i = 0; i < RES_STAGES; ++i) { mbar_init(RES_FULL(i), 128); mbar_init(RES_EMPTY(i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();  // generic-proxy smem writes above -> visible to the tensor core / TMA
@@ -340,47 +386,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
 
     const int my_tiles = (p.num_tiles - part + p.parts - 1) / p.parts;  // tiles part, part+parts, ...
 
-    if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            for (int it = 0; it < my_tiles; ++it) {
-                const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-                mbar_wait(RAW_EMPTY(st), ph ^ 1);
-                mbar_expect_tx(RAW_FULL(st), RAW_BYTES);
-                const int tile = part + it * p.parts;
-                tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));
+    if (wgrp == 0) {
+        reg_dec<REGS_CTRL>();
+        if (warp == 0) {
+            // ================================ TMA producer ================================
+            if (lane == 0) {
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
+                    mbar_wait(RAW_EMPTY(st), ph ^ 1);
+                    mbar_expect_tx(RAW_FULL(st), RAW_BYTES);
+                    const int tile = part + it * p.parts;
+                    tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));
+                }
             }
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-            const uint64_t ones_desc = make_desc(sbase + OFF_ONES, 128, 256);
-            const bool use_norm = (MK != MK_COSINE) || (p.k < TC_N);
-            uint32_t u = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                for (int i = 0; i < g_cnt; ++i) {
-                    if (!(act_mask >> i & 1)) continue;
-                    const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
-                    const int acc = u & 1, cph = (u >> 1) & 1;
-                    mbar_wait(A_FULL(ast), aph);
-                    mbar_wait(ACC_EMPTY(acc), cph ^ 1);
-                    tc_fence_after();
-                    const uint32_t a0 = sbase + OFF_AP + ast * AP_BYTES, b0 = sbase + OFF_BP + i * BP_BYTES;
-                    const uint32_t d = tmem_base + acc * TC_N;
-                    umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0, 128, 768), idesc, 0);              // x_hi . c_hi
-                    umma_tf32(d, make_desc(a0 + 256, 128, 512), make_desc(b0, 128, 768), idesc, 1);        // x_lo . c_hi
-                    umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0 + 256, 128, 768), idesc, 1);        // x_hi . c_lo
-                    if (use_norm) umma_tf32(d, ones_desc, make_desc(b0 + 512, 128, 768), idesc, 1);        // + ||c||^2
-                    umma_commit(A_EMPTY(ast));
-                    umma_commit(ACC_FULL(acc));
-                    ++u;
+        } else if (warp == 1) {
+            // ================================ MMA issuer ==================================
+            if (lane == 0) {
+                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+                const uint64_t ones_desc = make_desc(sbase + OFF_ONES, 128, 256);
+                const bool use_norm = (MK != MK_COSINE) || (p.k < TC_N);
+                uint32_t u = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    for (int i = 0; i < g_cnt; ++i) {
+                        if (!(act_mask >> i & 1)) continue;
+                        const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
+                        const int acc = u & 1, cph = (u >> 1) & 1;
+                        mbar_wait(A_FULL(ast), aph);
+                        mbar_wait(ACC_EMPTY(acc), cph ^ 1);
+                        tc_fence_after();
+                        const uint32_t a0 = sbase + OFF_AP + ast * AP_BYTES, b0 = sbase + OFF_BP + i * BP_BYTES;
+                        const uint32_t d = tmem_base + acc * TC_N;
+                        umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0, 128, 768), idesc, 0);              // x_hi . c_hi
+                        umma_tf32(d, make_desc(a0 + 256, 128, 512), make_desc(b0, 128, 768), idesc, 1);        // x_lo . c_hi
+                        umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0 + 256, 128, 768), idesc, 1);        // x_hi . c_lo
+                        if (use_norm) umma_tf32(d, ones_desc, make_desc(b0 + 512, 128, 768), idesc, 1);        // + ||c||^2
+                        umma_commit(A_EMPTY(ast));
+                        umma_commit(ACC_FULL(acc));
+                        ++u;
+                    }
                 }
             }
         }
-    } else if (warp < 6) {
-        // ================================ hi/lo splitter ==============================
-        const int r = (warp - 2) * 32 + lane;  // tile row
+    } else if (wgrp == 1) {
+        // ================================ hi/lo splitter + margin ======================
+        reg_dec<REGS_SPLIT>();
+        const int r = (warp - 4) * 32 + lane;  // tile row
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
@@ -389,6 +439,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
             for (int i = 0; i < g_cnt; ++i) {
                 if (!(act_mask >> i & 1)) continue;
                 const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
+                const int mg = u % MG_STAGES, mph = (u / MG_STAGES) & 1;
                 // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
                 const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
                 const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
@@ -402,68 +453,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 dst[0 * 8] = h0; dst[1 * 8] = h1; dst[2 * 8] = l0; dst[3 * 8] = l1;
                 fence_proxy_async();
                 mbar_arrive(A_FULL(ast));
+                // this row's error margin M = KAPPA * S and indicator scale H = 2^(40 - floor(log2 S)):
+                // (th - g) * H >= 1 for every representable g < th in the score range, th * H far from overflow
+                float nx2 = 0.f;
+                nx2 = fmaf(v0.x, v0.x, nx2); nx2 = fmaf(v0.y, v0.y, nx2); nx2 = fmaf(v0.z, v0.z, nx2); nx2 = fmaf(v0.w, v0.w, nx2);
+                nx2 = fmaf(v1.x, v1.x, nx2); nx2 = fmaf(v1.y, v1.y, nx2); nx2 = fmaf(v1.z, v1.z, nx2); nx2 = fmaf(v1.w, v1.w, nx2);
+                const float2 si = reinterpret_cast<const float2*>(sm + OFF_SINFO)[i];
+                float S;
+                if (MK == MK_COSINE) S = sqrt_approx(nx2) * 1.0000005f;
+                else { const float t = sqrt_approx(nx2) * 1.0000005f + si.x; S = t * t; }
+                // rows the pruning cannot be trusted on: NaN/Inf/huge/tiny magnitudes (negative M marks them)
+                const bool amb = (si.y != 0.f) || !(nx2 < 1e30f) || !(S > 1e-25f) || !(S < 1e30f);
+                const uint32_t sexp = (__float_as_uint(S) >> 23) & 0xFFu;
+                const float H = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
+                const float M = amb ? -1.0f : KAPPA * S;
+                mbar_wait(MG_EMPTY(mg), mph ^ 1);
+                reinterpret_cast<float2*>(sm + OFF_MG + mg * MG_BYTES)[r] = make_float2(H, M);
+                mbar_arrive(MG_FULL(mg));
                 ++u;
             }
             mbar_arrive(RAW_EMPTY(st));
         }
-    } else {
-        // ================================ epilogue ====================================
-        const int wg = (warp - 6) >> 2;             // warpgroup = TMEM accumulator
+    } else if (wgrp < 4) {
+        // ================================ scan ========================================
+        reg_inc<REGS_SCAN>();
+        const int acc = wgrp - 2;                   // TMEM accumulator of this warpgroup
         const int quarter = warp & 3;               // TMEM lane quarter this warp may read
         const int r = quarter * 32 + lane;          // tile row = TMEM lane
-        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N;
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-            const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
-            const bool live = row < p.n;
-            bool raw_seen = false;
             for (int i = 0; i < g_cnt; ++i) {
                 if (!(act_mask >> i & 1)) continue;
-                if ((int)(u & 1) != wg) { ++u; continue; }
+                if ((int)(u & 1) != acc) { ++u; continue; }
                 const int cph = (u >> 1) & 1;
+                const int mg = u % MG_STAGES, mph = (u / MG_STAGES) & 1;
+                const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
-                const int s = s0 + i;
-                if (!raw_seen) { mbar_wait(RAW_FULL(st), ph); raw_seen = true; }
-                // this row's sub-vector, margin and flags
-                ExactEval<MK> ev;
-                {
-                    const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
-                    const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
-                    const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
-                    ev.x.v[0] = v0.x; ev.x.v[1] = v0.y; ev.x.v[2] = v0.z; ev.x.v[3] = v0.w;
-                    ev.x.v[4] = v1.x; ev.x.v[5] = v1.y; ev.x.v[6] = v1.z; ev.x.v[7] = v1.w;
-                }
-                ev.init();
-                float nx2 = 0.f;
-#pragma unroll
-                for (int q = 0; q < TC_D; ++q) nx2 = fmaf(ev.x.v[q], ev.x.v[q], nx2);
-                const SubInfo si = p.sinfo[s];
-                float S;
-                if (MK == MK_COSINE) S = sqrtf(nx2);
-                else { float t = sqrtf(nx2) + sqrtf(si.cmax2); S = t * t; }
-                const float M = KAPPA * S;
-                // rows the pruning cannot be trusted on: NaN/Inf/huge/tiny magnitudes, hsdlib zero rule
-                bool amb = si.unsafe || !(nx2 < 1e30f) || !(S > 1e-25f) || !(S < 1e30f);
-                if (MK == MK_COSINE) amb = amb || !(ev.na >= FLT_MIN) || !ev.a_tail_ok;
-                // indicator scale H = 2^(40 - floor(log2 S)): (th - g) * H >= 1 for every representable g < th
-                // in the score range, and th * H stays far from overflow
-                const uint32_t sexp = (__float_as_uint(S) >> 23) & 0xFFu;
-                const float H = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
+                mbar_wait(MG_FULL(mg), mph);
+                const float2 hm = reinterpret_cast<const float2*>(sm + OFF_MG + mg * MG_BYTES)[r];
+                mbar_arrive(MG_EMPTY(mg));
+                const float H = hm.x, M = hm.y;
                 const float negH = -H, MH = M * H;
 
-                mbar_wait(ACC_FULL(wg), cph);
+                mbar_wait(ACC_FULL(acc), cph);
                 tc_fence_after();
                 float cm[8], ac[8];
-                const uint32_t tcol = tmem_base + tlane + wg * TC_N;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     uint32_t v[32];
                     tmem_ld32(tcol + c * 32, v);
                     tmem_ld_wait();
-                    if (DEBUG && p.dbg_scores && s == p.dbg_sub && live) {
+                    if (DEBUG) {
+                        const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
+                        if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) p.dbg_scores[(size_t)row * TC_N + c * 32 + q] = __uint_as_float(v[q]);
+                            for (int q = 0; q < 32; ++q) p.dbg_scores[(size_t)row * TC_N + c * 32 + q] = __uint_as_float(v[q]);
+                        }
                     }
                     float g[11];
 #pragma unroll
@@ -487,9 +533,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     ac[c] = (a0 + a1) + (a2 + a3);
                 }
                 tc_fence_before();
-                mbar_arrive(ACC_EMPTY(wg));  // TMEM accumulator may be overwritten by the next MMA chain
+                mbar_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
 
-                // ---- resolve: exactly one chunk and one group inside the margin?
+                // ---- exactly one chunk and one group inside the margin?
                 float mall = cm[0];
 #pragma unroll
                 for (int c = 1; c < 8; ++c) mall = fminf(mall, cm[c]);
@@ -502,20 +548,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     nfl += f ? 1 : 0;
                     if (f) { wsel = c; accw = ac[c]; }
                 }
-                const bool single = (nfl == 1) && (accw >= 32.f) && (accw <= 42.f) && (accw == floorf(accw));
-                amb = amb || !single;
+                const bool single = (M >= 0.f) && (nfl == 1) && (accw >= 32.f) && (accw <= 42.f) && (accw == floorf(accw));
+                const uint32_t res = single ? (uint32_t)(wsel * 32 + 3 * ((int)accw - 32)) : RES_AMBIGUOUS;
+                mbar_wait(RES_EMPTY(rs), rph ^ 1);
+                reinterpret_cast<uint32_t*>(sm + OFF_RES + rs * RES_BYTES)[r] = res;
+                mbar_arrive(RES_FULL(rs));
+            }
+        }
+    } else {
+        // ================================ resolve =====================================
+        reg_dec<REGS_RESOLVE>();
+        const int par = wgrp - 4;                   // units of this parity
+        const int r = (warp & 3) * 32 + lane;       // tile row
+        uint32_t u = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
+            const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
+            const bool live = row < p.n;
+            bool raw_seen = false;
+            for (int i = 0; i < g_cnt; ++i) {
+                if (!(act_mask >> i & 1)) continue;
+                if ((int)(u & 1) != par) { ++u; continue; }
+                const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
+                ++u;
+                const int s = s0 + i;
+                if (!raw_seen) { mbar_wait(RAW_FULL(st), ph); raw_seen = true; }
+                // this row's sub-vector
+                ExactEval<MK> ev;
+                {
+                    const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
+                    const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
+                    ev.x.v[0] = v0.x; ev.x.v[1] = v0.y; ev.x.v[2] = v0.z; ev.x.v[3] = v0.w;
+                    ev.x.v[4] = v1.x; ev.x.v[5] = v1.y; ev.x.v[6] = v1.z; ev.x.v[7] = v1.w;
+                }
+                ev.init();
+                mbar_wait(RES_FULL(rs), rph);
+                const uint32_t res = reinterpret_cast<const uint32_t*>(sm + OFF_RES + rs * RES_BYTES)[r];
+                mbar_arrive(RES_EMPTY(rs));
+                bool amb = res == RES_AMBIGUOUS;
+                if (MK == MK_COSINE) amb = amb || !(ev.na >= FLT_MIN) || !ev.a_tail_ok;  // hsdlib zero rule / tail check
                 const float* cb = reinterpret_cast<const float*>(sm + OFF_CB + i * CB_BYTES);
                 const float2* aux = reinterpret_cast<const float2*>(sm + OFF_AUX + i * AUX_BYTES);
                 uint32_t best = 0;
                 if (!amb) {
-                    const int t = (int)accw - 32;
-                    const int j0 = wsel * 32 + 3 * t;
+                    const int j0 = (int)res;
+                    const bool pair_only = (j0 & 31) == 30;  // the last group of a 32-column chunk has two members
                     best = (uint32_t)j0;
                     float bd = ev(cb, aux, j0);
 #pragma unroll
                     for (int q = 1; q < 3; ++q) {
                         const int j = j0 + q;
-                        if (j < p.k && !(t == 10 && q == 2)) {
+                        if (j < p.k && !(pair_only && q == 2)) {
                             const float dd = ev(cb, aux, j);
                             if (dd < bd) { bd = dd; best = (uint32_t)j; }
                         }
@@ -561,7 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 }
                 mbar_arrive(RAW_EMPTY(st));
             }
-            // units of this tile that belong to the other warpgroup still count one arrival each there
+            // units of this tile that belong to the other resolve warpgroup count one arrival each there
         }
     }
     tc_fence_before();

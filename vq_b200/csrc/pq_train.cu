@@ -20,8 +20,19 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 namespace {
+
+// VQB_TRACE=1: per-iteration host-side phase times on stderr (diagnostics only)
+inline bool trace_on() {
+    static const bool on = [] { const char* e = std::getenv("VQB_TRACE"); return e && *e && *e != '0'; }();
+    return on;
+}
+inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 constexpr int RX_THREADS = 256;   // one radix step = 256 consecutive rows
 constexpr int RX_STEPS = 8;       // steps per chunk
@@ -453,11 +464,13 @@ int vqb_pq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, s
     VQB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t d = dim / m;
 
+    const double t_enter = trace_on() ? now_ms() : 0.0;
     InputView xin;
     VQB_TRY(xin.bind(ctx, x, n * dim * sizeof(float)));
     TrainWs ws;
     VQB_TRY(ws.alloc(ctx, std::max<size_t>(n, 1), dim, m, k, o.update_mode == VQB_UPDATE_FAST ? 8 : 1));
     ws.n = n;
+    if (trace_on()) std::fprintf(stderr, "[vqb trace] bind + workspace alloc: %.3f ms\n", now_ms() - t_enter);
     TrainArgs a{static_cast<const float*>(xin.dev), n, dim, m, k, d, o.assign_mode, o.allreduce, o.allreduce_user,
                 o.row_offset};
 
@@ -481,10 +494,15 @@ int vqb_pq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, s
     for (size_t s = 0; s < m; ++s) active[s] = (int)s;
     std::vector<uint32_t> iters(m, 0), h_changed(m), h_counts(m * k);
     for (size_t it = 0; it < max_iters && !active.empty(); ++it) {
+        const double t0 = trace_on() ? now_ms() : 0.0;
         VQB_TRY(train_iteration(ctx, ws, a, active));
+        const double t1 = trace_on() ? now_ms() : 0.0;
         VQB_CUDA(ctx, cudaMemcpyAsync(h_changed.data(), ws.changed.p, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
         VQB_CUDA(ctx, cudaMemcpyAsync(h_counts.data(), ws.counts.p, m * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
         VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (trace_on())
+            std::fprintf(stderr, "[vqb trace] iter %zu: active=%zu enqueue=%.3f ms, wait=%.3f ms\n", it, active.size(),
+                         t1 - t0, now_ms() - t1);
         std::vector<long long> rows, dst;
         std::vector<int> subs;
         std::vector<int> next;
@@ -508,6 +526,7 @@ int vqb_pq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, s
     if (iters_run) std::memcpy(iters_run, iters.data(), m * 4);
     VQB_CUDA(ctx, cudaMemcpyAsync(codebooks, ws.cb.p, m * k * d * 4, cudaMemcpyDefault, ctx->stream));
     VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (trace_on()) std::fprintf(stderr, "[vqb trace] train total (before workspace free): %.3f ms\n", now_ms() - t_enter);
     return VQB_SUCCESS;
 }
 
