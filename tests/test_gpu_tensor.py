@@ -61,7 +61,12 @@ def debug_scores(eng, x, cb, sub, cosine):
 
 @pytest.mark.parametrize("scale", [1.0, 1e-3, 1e4])
 def test_tensor_scores_within_margin(eng, scale):
-    """|tcgen05 score - float64 score| must stay far inside the margin M = KAPPA * S used to prune."""
+    """|tcgen05 score - float64 score| must stay far inside the margin M = KAPPA * S used to prune.
+
+    Budget: pruning is sound while 2 * (err_tensor + err_reference) <= KAPPA * S.  The
+    reference's own rounding is <= 8e-7 * S (cosine, worst case), the tensor path's rigorous bound is
+    1.2e-6 * S (x_lo truncated by the tensor core, dropped x_lo.c_lo, c_lo rounding); KAPPA / 8 = 9.5e-7
+    is the measured-error guard that keeps the sum under KAPPA / 2 with room to spare."""
     n, dim, m, k = 20_000, 64, 8, 256
     x = mixture(n, dim, 5, scale=scale)
     cb = sample_codebooks(x, m, k, 6)
@@ -76,7 +81,7 @@ def test_tensor_scores_within_margin(eng, scale):
         err = np.abs(got - want).max(1) / S
         print(f"scale={scale} sub={sub} L2: max err/S = {err.max():.3e} (margin {KAPPA:.3e}), "
               f"re-scanned pairs = {rescans} of {n * m}")
-        assert err.max() <= KAPPA / 12
+        assert err.max() <= KAPPA / 8
         assert rescans <= 0.005 * n * m
         assert np.array_equal(codes, assign_train(eng, x, cb, 1))
         # cosine: -x.c/||c||
@@ -85,7 +90,7 @@ def test_tensor_scores_within_margin(eng, scale):
         S = np.sqrt((xs * xs).sum(1))
         err = np.abs(got - want).max(1) / S
         print(f"scale={scale} sub={sub} cos: max err/S = {err.max():.3e}, re-scanned pairs = {rescans} of {n * m}")
-        assert err.max() <= KAPPA / 12
+        assert err.max() <= KAPPA / 8
         assert rescans <= 0.005 * n * m
 
 

@@ -3,21 +3,26 @@
 // Replaces, for sub_dim == 8 and k <= 256, the per-pair distance loops of
 //   find_nearest_centroid      src/core/vector.rs:352-363   (training, squared L2)
 //   ProductQuantizer::quantize src/pq.rs:177-196            (encode: squared L2 / L2 / cosine)
-// by a dense contraction whose result is *decided* with the reference's own arithmetic:
+// by a dense contraction whose result is accepted only where it provably equals the reference's:
 //
 //   scores  S[row, j] = ||c_j||^2 - 2 x.c_j  (L2 kinds)   or   - x.c_j/||c_j||  (cosine)
 //           = one tcgen05.mma kind::tf32 M=128 N=256 chain per (128-row tile, subspace), K = 4 x 8:
-//             x_hi.c_hi + x_lo.c_hi + x_hi.c_lo (3xTF32 split, ~2^-21 relative) + [1,1,1].[n1,n2,n3]
-//             (the squared norm as three tf32 pieces); accumulators in TMEM (2 x 256 columns).
-//   epilogue one thread per row (= TMEM lane) reads its 256 scores with tcgen05.ld, takes minima
-//           over groups of three columns, and counts -- with saturating FMAs -- the groups that
-//           lie within a rigorous error margin M of the row minimum.  Exactly one such group
-//           (the overwhelmingly common case): its <= 3 centroids are evaluated with the
-//           reference's formula, operation for operation (distance.cuh), and compared with the
-//           reference's strict-'<' / lowest-index rule.  Otherwise (near-ties inside M, NaN/Inf,
-//           degenerate norms) the warp re-scans all k centroids of that row cooperatively, again
-//           with the reference's formula.  Every code is therefore decided by reference
-//           arithmetic; the tensor core only prunes candidates.
+//             x_hi.c_hi + x_hi.c_lo + x_lo.c_hi (3xTF32 split) + [1,1,1].[n1,n2,n3] (the squared norm as
+//             three tf32 pieces); accumulators in TMEM (2 x 256 columns).  x_hi is not materialised: the
+//             tensor core reads the fp32 TMA tile itself (SWIZZLE_128B descriptor) and truncates to tf32
+//             in hardware; only x_lo = x - trunc_tf32(x) (exact) is written by the splitter.
+//   scan    one thread per row (= TMEM lane) reads its 256 scores with tcgen05.ld (x16, double
+//           buffered), keeps the minima of the 64 groups of four columns (FMNMX3 + FMNMX), then -- once
+//           per row -- the row minimum and, with saturating FMAs and odd weights, the number and
+//           position of groups within a rigorous error margin M of it.  Exactly one such group: its
+//           index goes to the resolve stage; otherwise the row is "ambiguous".
+//   resolve re-scores the four candidates of that group in fp32 (conflict-free lane-rotated gathers
+//           of the raw codebook in shared memory) and accepts the best one only if it reproduces the
+//           row minimum (within M/2) and beats the runner-up by more than M.  Anything else -- near-ties
+//           inside M, NaN/Inf, degenerate norms, unsafe codebooks -- is decided by the warp re-scanning
+//           all k centroids of that row with the reference's own formula, operation for operation
+//           (distance.cuh), and its strict-'<' / lowest-index rule.  M bounds the tensor-core error plus
+//           the reference's own rounding, so an accepted code is the reference's code.
 //
 // Decomposition (B-stationary): a CTA owns 4 consecutive subspaces (32 floats = one 128-byte line
 // per row); their prepared codebooks stay in shared memory for the CTA's life and the CTA streams
@@ -25,15 +30,14 @@
 //
 // Warp roles (768 threads = 6 warpgroups, registers re-balanced with setmaxnreg):
 //   WG0  w0 TMA producer | w1 MMA issuer + TMEM owner | w2-3 idle
-//   WG1  hi/lo splitter: fp32 tile -> K-major no-swizzle tf32 operand tiles, + the row's error margin
+//   WG1  splitter: x_lo operand tile + the row's error margin
 //   WG2-3 scan: one warpgroup per TMEM accumulator; thread = row = TMEM lane; pure register work
-//         (tcgen05.ld, FMNMX3 minima, saturating-FMA indicators) -> one candidate group or "ambiguous"
-//   WG4-5 resolve: reference-arithmetic evaluation of the candidate group (or the full re-scan),
-//         code / f16 reconstruction stores
+//   WG4-5 resolve: fp32 re-score of the candidate group (or the full reference re-scan), code /
+//         f16 reconstruction stores
 // The per-unit chain split -> MMA -> scan -> resolve is a software pipeline over shared-memory rings;
-// all hand-offs are mbarriers; tcgen05.commit releases smem / signals TMEM.  Splitting the old
-// single epilogue role in two keeps ~5 warps per SM sub-partition busy instead of 2 (the v1 kernel
-// issued on 43 % of cycles with its epilogue warps stalled on their own dependency chains).
+// all hand-offs are mbarriers; tcgen05.commit releases smem / signals TMEM.  Waiting roles back off
+// with nanosleep so their polling does not take issue slots from the scan warps (r01b profile: 20 %
+// of all issued instructions were try_wait spins).
 #include "common.cuh"
 #include "distance.cuh"
 
@@ -48,9 +52,9 @@ constexpr int TC_G = 4;            // subspaces per CTA (4 * 8 floats = 128 B)
 constexpr int TC_N = 256;          // MMA N = centroid slots per subspace
 constexpr int TC_ROWS = 128;       // MMA M = rows per tile = TMEM lanes
 constexpr int RAW_STAGES = 3;
-constexpr int A_STAGES = 3;
+constexpr int A_STAGES = 4;        // splitter -> MMA: x_lo operand tiles
 constexpr int MG_STAGES = 4;       // splitter -> scan: per-row margin
-constexpr int RES_STAGES = 4;      // scan -> resolve: per-row candidate
+constexpr int RES_STAGES = 4;      // scan -> resolve: per-row candidate group
 constexpr int TC_THREADS = 768;
 // setmaxnreg budget: the pool is what the CTA was launched with (768 threads x 80 registers = 61440), so
 // 128*24 + 128*48 + 256*128 + 256*72 = 60416 must not exceed it or the last setmaxnreg.inc never returns
@@ -60,19 +64,21 @@ static_assert(128 * REGS_CTRL + 128 * REGS_SPLIT + 256 * REGS_SCAN + 256 * REGS_
 
 constexpr uint32_t RAW_BYTES = TC_ROWS * 128;           // 16 KB per stage
 constexpr uint32_t BP_BYTES = 32 * 6 * 128;             // 24 KB: [32 row groups][6 k-chunks][8 rows][16 B]
-constexpr uint32_t CB_BYTES = TC_N * TC_D * 4;          // 8 KB raw f32 codebook
-constexpr uint32_t AUX_BYTES = TC_N * 8;                // 2 KB (nb, sb) per centroid (cosine)
-constexpr uint32_t AP_BYTES = 16 * 4 * 128;             // 8 KB: [16 row groups][4 k-chunks][8 rows][16 B]
+constexpr uint32_t CB_BYTES = TC_N * TC_D * 4;          // 8 KB raw f32 codebook, row-major
+constexpr uint32_t AUX_BYTES = TC_N * 8;                // 2 KB (nb, sb) per centroid (cosine, exact path)
+constexpr uint32_t RINV_BYTES = TC_N * 4;               // 1 KB -1/||c|| per centroid (cosine, fp32 re-score)
+constexpr uint32_t AP_BYTES = 16 * 2 * 128;             // 4 KB: [16 row groups][2 k-chunks][8 rows][16 B]
 constexpr uint32_t ONES_BYTES = 16 * 2 * 128;           // 4 KB
 constexpr uint32_t MG_BYTES = TC_ROWS * 8;              // float2 {H, M} per row
-constexpr uint32_t RES_BYTES = TC_ROWS * 4;             // u32 candidate per row
-constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES;  // per-subspace prepared image in HBM
+constexpr uint32_t RES_BYTES = TC_ROWS * 8;             // float2 {row minimum, M | group index} per row
+constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES + RINV_BYTES;  // per-subspace prepared image in HBM
 
 constexpr uint32_t OFF_RAW = 0;
 constexpr uint32_t OFF_BP = OFF_RAW + RAW_STAGES * RAW_BYTES;
 constexpr uint32_t OFF_CB = OFF_BP + TC_G * BP_BYTES;
 constexpr uint32_t OFF_AUX = OFF_CB + TC_G * CB_BYTES;
-constexpr uint32_t OFF_AP = OFF_AUX + TC_G * AUX_BYTES;
+constexpr uint32_t OFF_RINV = OFF_AUX + TC_G * AUX_BYTES;
+constexpr uint32_t OFF_AP = OFF_RINV + TC_G * RINV_BYTES;
 constexpr uint32_t OFF_ONES = OFF_AP + A_STAGES * AP_BYTES;
 constexpr uint32_t OFF_MG = OFF_ONES + ONES_BYTES;
 constexpr uint32_t OFF_RES = OFF_MG + MG_STAGES * MG_BYTES;
@@ -80,7 +86,8 @@ constexpr uint32_t OFF_SINFO = OFF_RES + RES_STAGES * RES_BYTES;  // TC_G x {sqr
 constexpr uint32_t OFF_BAR = OFF_SINFO + 64;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // barriers + slack for the 1024-byte alignment
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
-constexpr uint32_t RES_AMBIGUOUS = 0xFFFFFFFFu;
+static_assert(OFF_CB % 128 == 0 && OFF_AP % 128 == 0, "operand tiles must be 128-byte aligned");
+constexpr uint32_t RES_AMBIGUOUS = 0x80000000u;         // sign bit of the margin word
 
 template <int D>
 struct RegArr {
@@ -94,10 +101,11 @@ struct SubInfo {        // per subspace, written by the prepare kernel
 };
 
 // margin constants: M = KAPPA * S, S = (||x|| + max||c||)^2 for the L2 kinds, ||x|| for cosine.
-// Error budget behind it (DESIGN.md "tensor assignment: error bound"): 3xTF32 split 3*2^-22, fp32
+// Error budget behind it: x = x_hi + x_lo exactly, x_lo truncated to tf32 by the tensor
+// core (<= 2^-21 |x_i|), c = c_hi + c_lo + (<= 2^-23 |c_i|), dropped x_lo.c_lo (<= 2^-21), fp32
 // accumulation of <= 32 products, the norm pieces, and the reference's own rounding (<= 11 ulp of d).
-// Measured on B200 (tests/test_gpu_tensor.py::test_tensor_scores_within_margin): |score - f64| <= 5.3e-7 * S.
-constexpr float KAPPA = 1.0f / 131072.0f;  // 2^-17 = 7.6e-6 >= 2 * (5.3e-7 + 6.6e-7) with 3x to spare
+// Measured on B200 (tests/test_gpu_tensor.py::test_tensor_scores_within_margin).
+constexpr float KAPPA = 1.0f / 131072.0f;  // 2^-17 = 7.6e-6
 
 // ------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,6 +122,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(bar), "r"(parity), "r"(0x4000u)  // suspend-time hint (ns): waiters sleep in hardware, not in the issue slots
             : "memory");
+    }
+}
+// waiting roles that are not on the critical path: poll, then sleep between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(64);
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -154,6 +177,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
+// K-major SWIZZLE_128B (the layout TMA writes): 8-row atoms of 1024 B, the K offset inside the 128-byte
+// row is added to the start address and swizzled by the hardware (address bits 4-6 ^= bits 7-9).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -165,6 +194,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// tcgen05.wait::ld tied to the destination registers, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ float to_tf32(float x) {  // round-to-nearest tf32, low 13 bits zero
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -209,9 +254,11 @@ __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ c
     if (!finite) atomicOr(&bad, 1u);
     float b[TC_D];
     float npiece[3] = {0.f, 0.f, 0.f};
+    float nrinv = 0.0f;
     if (MK == MK_COSINE) {
         // scores = -x.c/||c||;  ||c||^2 < FLT_MIN counts as a zero vector (cosine.c:38-45): score 0
         double inv = (finite && n2 >= (double)FLT_MIN) ? 1.0 / sqrt(n2) : 0.0;
+        nrinv = (float)(-inv);
 #pragma unroll
         for (int i = 0; i < TC_D; ++i) b[i] = finite ? (float)(-(double)c[i] * inv) : 0.0f;
     } else {
@@ -248,6 +295,7 @@ __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ c
         float nb = hsd_cosine_norm<TC_D>(ca, TC_D, tok);
         float2* aux = reinterpret_cast<float2*>(img + BP_BYTES + CB_BYTES + j * 8);
         *aux = make_float2(nb, __fsqrt_rn(nb));
+        reinterpret_cast<float*>(img + BP_BYTES + CB_BYTES + AUX_BYTES)[j] = nrinv;
     }
     red[j] = (real && finite) ? (float)n2 : 0.0f;
     __syncthreads();
@@ -311,6 +359,16 @@ __device__ __forceinline__ void store_code(void* codes, uint32_t code_bytes, siz
 }
 
 // ----------------------------------------------------------------------------------- main kernel
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// minima of the four groups of four columns held by one x16 TMEM load
+__device__ __forceinline__ void group_min4(const uint32_t (&v)[16], float* g) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        g[q] = fminf(fmin3(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2])),
+                     __uint_as_float(v[4 * q + 3]));
+}
+
 template <int MK, bool DEBUG>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -348,6 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         if (!p.active || p.active[s0 + i]) act_mask |= 1u << i;
     const int n_act = __popc(act_mask);
     if (n_act == 0) return;
+    const int last_act = 31 - __clz(act_mask);
 
     // ---- one-time setup: prepared codebooks -> smem, constant ones tile, barriers, TMEM
     for (int i = 0; i < TC_G; ++i) {
@@ -356,9 +415,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         float4* dbp = reinterpret_cast<float4*>(sm + OFF_BP + i * BP_BYTES);
         float4* dcb = reinterpret_cast<float4*>(sm + OFF_CB + i * CB_BYTES);
         float4* dax = reinterpret_cast<float4*>(sm + OFF_AUX + i * AUX_BYTES);
+        float4* dri = reinterpret_cast<float4*>(sm + OFF_RINV + i * RINV_BYTES);
         for (int t = threadIdx.x; t < (int)(BP_BYTES / 16); t += TC_THREADS) dbp[t] = __ldg(src + t);
         for (int t = threadIdx.x; t < (int)(CB_BYTES / 16); t += TC_THREADS) dcb[t] = __ldg(src + BP_BYTES / 16 + t);
         for (int t = threadIdx.x; t < (int)(AUX_BYTES / 16); t += TC_THREADS) dax[t] = __ldg(src + (BP_BYTES + CB_BYTES) / 16 + t);
+        for (int t = threadIdx.x; t < (int)(RINV_BYTES / 16); t += TC_THREADS)
+            dri[t] = __ldg(src + (BP_BYTES + CB_BYTES + AUX_BYTES) / 16 + t);
     }
     for (int t = threadIdx.x; t < (int)(ONES_BYTES / 16); t += TC_THREADS) {
         // [16 groups][2 chunks][8 rows][16 B]: chunk 0 = (1,1,1,0), chunk 1 = 0
@@ -370,7 +432,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         reinterpret_cast<float2*>(sm + OFF_SINFO)[threadIdx.x] = make_float2(sqrtf(si.cmax2) * 1.0000005f, si.unsafe ? 1.0f : 0.0f);
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(RAW_FULL(i), 1); mbar_init(RAW_EMPTY(i), 128 + 128 * n_act); }
+        // a raw tile is released by the splitter (128), every resolve unit (128 each) and the last MMA that read it (1)
+        for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(RAW_FULL(i), 1); mbar_init(RAW_EMPTY(i), 128 + 128 * n_act + 1); }
         for (int i = 0; i < A_STAGES; ++i) { mbar_init(A_FULL(i), 128); mbar_init(A_EMPTY(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 128); }
         for (int i = 0; i < MG_STAGES; ++i) { mbar_init(MG_FULL(i), 128); mbar_init(MG_EMPTY(i), 128); }
@@ -393,7 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
             if (lane == 0) {
                 for (int it = 0; it < my_tiles; ++it) {
                     const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-                    mbar_wait(RAW_EMPTY(st), ph ^ 1);
+                    mbar_wait_relaxed(RAW_EMPTY(st), ph ^ 1);
                     mbar_expect_tx(RAW_FULL(st), RAW_BYTES);
                     const int tile = part + it * p.parts;
                     tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));
@@ -407,34 +470,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 const bool use_norm = (MK != MK_COSINE) || (p.k < TC_N);
                 uint32_t u = 0;
                 for (int it = 0; it < my_tiles; ++it) {
+                    const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
+                    mbar_wait(RAW_FULL(st), ph);   // TMA bytes have landed: the tensor core reads x_hi from the tile itself
                     for (int i = 0; i < g_cnt; ++i) {
                         if (!(act_mask >> i & 1)) continue;
                         const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
                         const int acc = u & 1, cph = (u >> 1) & 1;
-                        mbar_wait(A_FULL(ast), aph);
                         mbar_wait(ACC_EMPTY(acc), cph ^ 1);
                         tc_fence_after();
+                        const uint64_t xhi = make_desc_sw128(sbase + OFF_RAW + st * RAW_BYTES + i * 32);
                         const uint32_t a0 = sbase + OFF_AP + ast * AP_BYTES, b0 = sbase + OFF_BP + i * BP_BYTES;
                         const uint32_t d = tmem_base + acc * TC_N;
-                        umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0, 128, 768), idesc, 0);              // x_hi . c_hi
-                        umma_tf32(d, make_desc(a0 + 256, 128, 512), make_desc(b0, 128, 768), idesc, 1);        // x_lo . c_hi
-                        umma_tf32(d, make_desc(a0, 128, 512), make_desc(b0 + 256, 128, 768), idesc, 1);        // x_hi . c_lo
+                        umma_tf32(d, xhi, make_desc(b0, 128, 768), idesc, 0);                                  // x_hi . c_hi
+                        umma_tf32(d, xhi, make_desc(b0 + 256, 128, 768), idesc, 1);                            // x_hi . c_lo
                         if (use_norm) umma_tf32(d, ones_desc, make_desc(b0 + 512, 128, 768), idesc, 1);        // + ||c||^2
+                        mbar_wait(A_FULL(ast), aph);
+                        tc_fence_after();
+                        umma_tf32(d, make_desc(a0, 128, 256), make_desc(b0, 128, 768), idesc, 1);              // x_lo . c_hi
                         umma_commit(A_EMPTY(ast));
                         umma_commit(ACC_FULL(acc));
+                        if (i == last_act) umma_commit(RAW_EMPTY(st));
                         ++u;
                     }
                 }
             }
         }
     } else if (wgrp == 1) {
-        // ================================ hi/lo splitter + margin ======================
+        // ================================ splitter: x_lo + margin ======================
         reg_dec<REGS_SPLIT>();
         const int r = (warp - 4) * 32 + lane;  // tile row
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-            mbar_wait(RAW_FULL(st), ph);
+            mbar_wait_relaxed(RAW_FULL(st), ph);
             const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
             for (int i = 0; i < g_cnt; ++i) {
                 if (!(act_mask >> i & 1)) continue;
@@ -443,14 +511,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
                 const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
                 const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
-                float4 h0, h1, l0, l1;
-                h0.x = to_tf32(v0.x); h0.y = to_tf32(v0.y); h0.z = to_tf32(v0.z); h0.w = to_tf32(v0.w);
-                h1.x = to_tf32(v1.x); h1.y = to_tf32(v1.y); h1.z = to_tf32(v1.z); h1.w = to_tf32(v1.w);
-                l0.x = to_tf32(v0.x - h0.x); l0.y = to_tf32(v0.y - h0.y); l0.z = to_tf32(v0.z - h0.z); l0.w = to_tf32(v0.w - h0.w);
-                l1.x = to_tf32(v1.x - h1.x); l1.y = to_tf32(v1.y - h1.y); l1.z = to_tf32(v1.z - h1.z); l1.w = to_tf32(v1.w - h1.w);
-                mbar_wait(A_EMPTY(ast), aph ^ 1);
-                float4* dst = reinterpret_cast<float4*>(sm + OFF_AP + ast * AP_BYTES + (r >> 3) * 512 + (r & 7) * 16);
-                dst[0 * 8] = h0; dst[1 * 8] = h1; dst[2 * 8] = l0; dst[3 * 8] = l1;
+                // x_lo = x - trunc_tf32(x): exact, and exactly what the tensor core leaves out when it reads x as tf32
+                float4 l0, l1;
+                l0.x = v0.x - __uint_as_float(__float_as_uint(v0.x) & 0xFFFFE000u);
+                l0.y = v0.y - __uint_as_float(__float_as_uint(v0.y) & 0xFFFFE000u);
+                l0.z = v0.z - __uint_as_float(__float_as_uint(v0.z) & 0xFFFFE000u);
+                l0.w = v0.w - __uint_as_float(__float_as_uint(v0.w) & 0xFFFFE000u);
+                l1.x = v1.x - __uint_as_float(__float_as_uint(v1.x) & 0xFFFFE000u);
+                l1.y = v1.y - __uint_as_float(__float_as_uint(v1.y) & 0xFFFFE000u);
+                l1.z = v1.z - __uint_as_float(__float_as_uint(v1.z) & 0xFFFFE000u);
+                l1.w = v1.w - __uint_as_float(__float_as_uint(v1.w) & 0xFFFFE000u);
+                mbar_wait_relaxed(A_EMPTY(ast), aph ^ 1);
+                float4* dst = reinterpret_cast<float4*>(sm + OFF_AP + ast * AP_BYTES + (r >> 3) * 256 + (r & 7) * 16);
+                dst[0] = l0; dst[8] = l1;
                 fence_proxy_async();
                 mbar_arrive(A_FULL(ast));
                 // this row's error margin M = KAPPA * S and indicator scale H = 2^(40 - floor(log2 S)):
@@ -462,12 +535,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 float S;
                 if (MK == MK_COSINE) S = sqrt_approx(nx2) * 1.0000005f;
                 else { const float t = sqrt_approx(nx2) * 1.0000005f + si.x; S = t * t; }
-                // rows the pruning cannot be trusted on: NaN/Inf/huge/tiny magnitudes (negative M marks them)
-                const bool amb = (si.y != 0.f) || !(nx2 < 1e30f) || !(S > 1e-25f) || !(S < 1e30f);
+                // rows the pruning cannot be trusted on: NaN/Inf/huge/tiny magnitudes (negative M marks them);
+                // cosine rows near hsdlib's zero-vector rule (||x||^2 < FLT_MIN, cosine.c:38-45) go the exact way too
+                bool amb = (si.y != 0.f) || !(nx2 < 1e30f) || !(S > 1e-25f) || !(S < 1e30f);
+                if (MK == MK_COSINE) amb = amb || !(nx2 > 4.0f * FLT_MIN);
                 const uint32_t sexp = (__float_as_uint(S) >> 23) & 0xFFu;
                 const float H = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
                 const float M = amb ? -1.0f : KAPPA * S;
-                mbar_wait(MG_EMPTY(mg), mph ^ 1);
+                mbar_wait_relaxed(MG_EMPTY(mg), mph ^ 1);
                 reinterpret_cast<float2*>(sm + OFF_MG + mg * MG_BYTES)[r] = make_float2(H, M);
                 mbar_arrive(MG_FULL(mg));
                 ++u;
@@ -490,68 +565,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 const int mg = u % MG_STAGES, mph = (u / MG_STAGES) & 1;
                 const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
-                mbar_wait(MG_FULL(mg), mph);
-                const float2 hm = reinterpret_cast<const float2*>(sm + OFF_MG + mg * MG_BYTES)[r];
-                mbar_arrive(MG_EMPTY(mg));
-                const float H = hm.x, M = hm.y;
-                const float negH = -H, MH = M * H;
 
                 mbar_wait(ACC_FULL(acc), cph);
                 tc_fence_after();
-                float cm[8], ac[8];
+                // ---- 256 scores -> 64 minima of four columns; the next x16 load is in flight while one is reduced
+                float gm[64];
+                uint32_t va[16], vb[16];
+                tmem_ld16(tcol, va);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tcol + c * 32, v);
-                    tmem_ld_wait();
+                for (int c = 0; c < 16; c += 2) {
+                    tmem_ld_wait16(va);
+                    tmem_ld16(tcol + (c + 1) * 16, vb);
                     if (DEBUG) {
                         const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
                         if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
 #pragma unroll
-                            for (int q = 0; q < 32; ++q) p.dbg_scores[(size_t)row * TC_N + c * 32 + q] = __uint_as_float(v[q]);
+                            for (int q = 0; q < 16; ++q) p.dbg_scores[(size_t)row * TC_N + c * 16 + q] = __uint_as_float(va[q]);
                         }
                     }
-                    float g[11];
+                    group_min4(va, &gm[4 * c]);
+                    tmem_ld_wait16(vb);
+                    if (c + 2 < 16) tmem_ld16(tcol + (c + 2) * 16, va);
+                    if (DEBUG) {
+                        const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
+                        if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
 #pragma unroll
-                    for (int t = 0; t < 10; ++t)
-                        g[t] = fminf(fminf(__uint_as_float(v[3 * t]), __uint_as_float(v[3 * t + 1])), __uint_as_float(v[3 * t + 2]));
-                    g[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-                    const float m0 = fminf(fminf(g[0], g[1]), g[2]), m1 = fminf(fminf(g[3], g[4]), g[5]);
-                    const float m2 = fminf(fminf(g[6], g[7]), g[8]), m3 = fminf(g[9], g[10]);
-                    const float mc = fminf(fminf(fminf(m0, m1), m2), m3);
-                    const float thH = fmaf(mc, H, MH);  // (mc + M) * H
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                    for (int t = 0; t < 11; ++t) {
-                        const float w = (float)(32 + t), ind = fsat_ind(g[t], negH, thH);
-                        if ((t & 3) == 0) a0 = fmaf(ind, w, a0);
-                        if ((t & 3) == 1) a1 = fmaf(ind, w, a1);
-                        if ((t & 3) == 2) a2 = fmaf(ind, w, a2);
-                        if ((t & 3) == 3) a3 = fmaf(ind, w, a3);
+                            for (int q = 0; q < 16; ++q) p.dbg_scores[(size_t)row * TC_N + (c + 1) * 16 + q] = __uint_as_float(vb[q]);
+                        }
                     }
-                    cm[c] = mc;
-                    ac[c] = (a0 + a1) + (a2 + a3);
+                    group_min4(vb, &gm[4 * c + 4]);
                 }
                 tc_fence_before();
                 mbar_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
 
-                // ---- exactly one chunk and one group inside the margin?
-                float mall = cm[0];
+                // ---- row minimum
+                float t1[22];
 #pragma unroll
-                for (int c = 1; c < 8; ++c) mall = fminf(mall, cm[c]);
-                const float thr = mall + M;
-                int nfl = 0, wsel = 0;
-                float accw = 0.f;
+                for (int q = 0; q < 21; ++q) t1[q] = fmin3(gm[3 * q], gm[3 * q + 1], gm[3 * q + 2]);
+                t1[21] = gm[63];
+                float t2[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const bool f = cm[c] < thr;
-                    nfl += f ? 1 : 0;
-                    if (f) { wsel = c; accw = ac[c]; }
+                for (int q = 0; q < 7; ++q) t2[q] = fmin3(t1[3 * q], t1[3 * q + 1], t1[3 * q + 2]);
+                t2[7] = t1[21];
+                const float mall = fmin3(fmin3(t2[0], t2[1], t2[2]), fmin3(t2[3], t2[4], t2[5]), fminf(t2[6], t2[7]));
+
+                mbar_wait(MG_FULL(mg), mph);
+                const float2 hm = reinterpret_cast<const float2*>(sm + OFF_MG + mg * MG_BYTES)[r];
+                mbar_arrive(MG_EMPTY(mg));
+                const float H = hm.x, M = hm.y;
+                const float negH = -H;
+                const float thH = fmaf(mall, H, M * H);  // (mall + M) * H
+
+                // ---- groups within M of the minimum: indicator = sat((th - g) * H) in {0, 1}; the odd weights
+                // 129 + 2t make the sum decode to t iff exactly one group is flagged (two flagged groups sum to
+                // >= 258; a fractional indicator -- g within S * 2^-40 of the threshold -- cannot produce an odd
+                // integer together with the always-full indicator of the minimum, and the resolve stage re-checks
+                // the decoded group against the row minimum anyway)
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 64; ++t) {
+                    const float w = (float)(129 + 2 * t), ind = fsat_ind(gm[t], negH, thH);
+                    if ((t & 3) == 0) a0 = fmaf(ind, w, a0);
+                    if ((t & 3) == 1) a1 = fmaf(ind, w, a1);
+                    if ((t & 3) == 2) a2 = fmaf(ind, w, a2);
+                    if ((t & 3) == 3) a3 = fmaf(ind, w, a3);
                 }
-                const bool single = (M >= 0.f) && (nfl == 1) && (accw >= 32.f) && (accw <= 42.f) && (accw == floorf(accw));
-                const uint32_t res = single ? (uint32_t)(wsel * 32 + 3 * ((int)accw - 32)) : RES_AMBIGUOUS;
+                const float accw = (a0 + a1) + (a2 + a3);
+                const int wi = (int)accw;
+                const bool single = (M >= 0.f) && (accw >= 129.f) && (accw <= 255.f) && (accw == floorf(accw)) && (wi & 1);
+                // result word: the margin with its low six mantissa bits replaced by the group index; sign bit = ambiguous
+                const uint32_t word = single ? ((__float_as_uint(M) & ~63u) | (uint32_t)((wi - 129) >> 1)) : RES_AMBIGUOUS;
                 mbar_wait(RES_EMPTY(rs), rph ^ 1);
-                reinterpret_cast<uint32_t*>(sm + OFF_RES + rs * RES_BYTES)[r] = res;
+                reinterpret_cast<float2*>(sm + OFF_RES + rs * RES_BYTES)[r] = make_float2(mall, __uint_as_float(word));
                 mbar_arrive(RES_FULL(rs));
             }
         }
@@ -560,6 +645,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         reg_dec<REGS_RESOLVE>();
         const int par = wgrp - 4;                   // units of this parity
         const int r = (warp & 3) * 32 + lane;       // tile row
+        // lane-rotated candidate order: the eight lanes of a quarter-warp read eight different 16-byte
+        // slots of their (arbitrary) 128-byte candidate groups -> conflict-free LDS.128 gathers
+        const int h0 = lane & 1, rot = (lane >> 1) & 3;
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
@@ -572,66 +660,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
                 const int s = s0 + i;
-                if (!raw_seen) { mbar_wait(RAW_FULL(st), ph); raw_seen = true; }
-                // this row's sub-vector
-                ExactEval<MK> ev;
-                {
-                    const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
-                    const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
-                    const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
-                    ev.x.v[0] = v0.x; ev.x.v[1] = v0.y; ev.x.v[2] = v0.z; ev.x.v[3] = v0.w;
-                    ev.x.v[4] = v1.x; ev.x.v[5] = v1.y; ev.x.v[6] = v1.z; ev.x.v[7] = v1.w;
-                }
-                ev.init();
-                mbar_wait(RES_FULL(rs), rph);
-                const uint32_t res = reinterpret_cast<const uint32_t*>(sm + OFF_RES + rs * RES_BYTES)[r];
+                if (!raw_seen) { mbar_wait_relaxed(RAW_FULL(st), ph); raw_seen = true; }
+                // this row's sub-vector, halves in this lane's gather order
+                const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
+                const float4 xa = *reinterpret_cast<const float4*>(rawrow + (((2 * i + h0) ^ (r & 7)) << 4));
+                const float4 xb = *reinterpret_cast<const float4*>(rawrow + (((2 * i + (h0 ^ 1)) ^ (r & 7)) << 4));
+                mbar_wait_relaxed(RES_FULL(rs), rph);
+                const float2 rv = reinterpret_cast<const float2*>(sm + OFF_RES + rs * RES_BYTES)[r];
                 mbar_arrive(RES_EMPTY(rs));
-                bool amb = res == RES_AMBIGUOUS;
-                if (MK == MK_COSINE) amb = amb || !(ev.na >= FLT_MIN) || !ev.a_tail_ok;  // hsdlib zero rule / tail check
+                const uint32_t word = __float_as_uint(rv.y);
                 const float* cb = reinterpret_cast<const float*>(sm + OFF_CB + i * CB_BYTES);
                 const float2* aux = reinterpret_cast<const float2*>(sm + OFF_AUX + i * AUX_BYTES);
                 uint32_t best = 0;
-                if (!amb) {
-                    const int j0 = (int)res;
-                    const bool pair_only = (j0 & 31) == 30;  // the last group of a 32-column chunk has two members
-                    best = (uint32_t)j0;
-                    float bd = ev(cb, aux, j0);
+                bool amb = true;
+                if (!(word & RES_AMBIGUOUS)) {
+                    const int t = (int)(word & 63u);
+                    const float M = __uint_as_float(word & ~63u);
+                    const uint8_t* gbase = reinterpret_cast<const uint8_t*>(cb) + t * 128;
+                    const float* nri = reinterpret_cast<const float*>(sm + OFF_RINV + i * RINV_BYTES) + 4 * t;
+                    float b1 = __int_as_float(0x7f800000), b2 = b1;
+                    int jb = 0;
 #pragma unroll
-                    for (int q = 1; q < 3; ++q) {
-                        const int j = j0 + q;
-                        if (j < p.k && !(pair_only && q == 2)) {
-                            const float dd = ev(cb, aux, j);
-                            if (dd < bd) { bd = dd; best = (uint32_t)j; }
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int q = (ii + rot) & 3;
+                        const float4 ca = *reinterpret_cast<const float4*>(gbase + q * 32 + h0 * 16);
+                        const float4 cc = *reinterpret_cast<const float4*>(gbase + q * 32 + (h0 ^ 1) * 16);
+                        float sc;
+                        if (MK == MK_COSINE) {
+                            float dot = ca.x * xa.x;
+                            dot = fmaf(ca.y, xa.y, dot); dot = fmaf(ca.z, xa.z, dot); dot = fmaf(ca.w, xa.w, dot);
+                            dot = fmaf(cc.x, xb.x, dot); dot = fmaf(cc.y, xb.y, dot); dot = fmaf(cc.z, xb.z, dot); dot = fmaf(cc.w, xb.w, dot);
+                            sc = dot * nri[q];
+                        } else {
+                            float e = ca.x - xa.x; sc = e * e;
+                            e = ca.y - xa.y; sc = fmaf(e, e, sc); e = ca.z - xa.z; sc = fmaf(e, e, sc); e = ca.w - xa.w; sc = fmaf(e, e, sc);
+                            e = cc.x - xb.x; sc = fmaf(e, e, sc); e = cc.y - xb.y; sc = fmaf(e, e, sc);
+                            e = cc.z - xb.z; sc = fmaf(e, e, sc); e = cc.w - xb.w; sc = fmaf(e, e, sc);
                         }
+                        if (4 * t + q >= p.k) sc = __int_as_float(0x7f800000);  // padding slot
+                        b2 = fminf(b2, fmaxf(b1, sc));
+                        if (sc < b1) jb = q;
+                        b1 = fminf(b1, sc);
                     }
+                    float ref = rv.x;  // tensor-core row minimum: ||c||^2 - 2 x.c  (L2 kinds)  or  -x.c/||c||
+                    if (MK != MK_COSINE) {
+                        float nx2 = xa.x * xa.x;
+                        nx2 = fmaf(xa.y, xa.y, nx2); nx2 = fmaf(xa.z, xa.z, nx2); nx2 = fmaf(xa.w, xa.w, nx2);
+                        nx2 = fmaf(xb.x, xb.x, nx2); nx2 = fmaf(xb.y, xb.y, nx2); nx2 = fmaf(xb.z, xb.z, nx2); nx2 = fmaf(xb.w, xb.w, nx2);
+                        ref += nx2;
+                    }
+                    // accept iff this group really holds the row minimum and its best beats its runner-up by more than M
+                    const bool ok = (b1 - ref <= 0.5f * M) && (ref - b1 <= 0.5f * M) && (b2 - b1 > M);
+                    amb = !ok;
+                    best = (uint32_t)(4 * t + jb);
                 }
-                // ---- rows inside the margin: the warp scans all k centroids with the reference formula
+                // ---- everything else: the warp scans all k centroids of the row with the reference formula
                 uint32_t todo = __ballot_sync(0xFFFFFFFFu, amb && live);
                 if (DEBUG && p.dbg_stats && lane == 0 && todo) atomicAdd(p.dbg_stats, (unsigned long long)__popc(todo));
-                while (todo) {
-                    const int L = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    ExactEval<MK> eo;
+                if (todo) {
+                    ExactEval<MK> ev;  // this row's sub-vector in natural order
+                    ev.x.v[0] = h0 ? xb.x : xa.x; ev.x.v[1] = h0 ? xb.y : xa.y; ev.x.v[2] = h0 ? xb.z : xa.z; ev.x.v[3] = h0 ? xb.w : xa.w;
+                    ev.x.v[4] = h0 ? xa.x : xb.x; ev.x.v[5] = h0 ? xa.y : xb.y; ev.x.v[6] = h0 ? xa.z : xb.z; ev.x.v[7] = h0 ? xa.w : xb.w;
+                    while (todo) {
+                        const int L = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        ExactEval<MK> eo;
 #pragma unroll
-                    for (int q = 0; q < TC_D; ++q) eo.x.v[q] = __shfl_sync(0xFFFFFFFFu, ev.x.v[q], L);
-                    eo.init();
-                    float bd = __int_as_float(0x7f800000);
-                    uint32_t bj = 0xFFFFFFFFu;
-                    bool d0nan = false;
-                    for (int j = lane; j < p.k; j += 32) {
-                        float dd = eo(cb, aux, j);
-                        if (j == 0) d0nan = isnan(dd);
-                        if (isnan(dd)) dd = __int_as_float(0x7f800000);
-                        if (bj == 0xFFFFFFFFu || dd < bd) { bd = dd; bj = (uint32_t)j; }
-                    }
+                        for (int q = 0; q < TC_D; ++q) eo.x.v[q] = __shfl_sync(0xFFFFFFFFu, ev.x.v[q], L);
+                        eo.init();
+                        float bd = __int_as_float(0x7f800000);
+                        uint32_t bj = 0xFFFFFFFFu;
+                        bool d0nan = false;
+                        for (int j = lane; j < p.k; j += 32) {
+                            float dd = eo(cb, aux, j);
+                            if (j == 0) d0nan = isnan(dd);
+                            if (isnan(dd)) dd = __int_as_float(0x7f800000);
+                            if (bj == 0xFFFFFFFFu || dd < bd) { bd = dd; bj = (uint32_t)j; }
+                        }
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        const float od = __shfl_xor_sync(0xFFFFFFFFu, bd, off);
-                        const uint32_t oj = __shfl_xor_sync(0xFFFFFFFFu, bj, off);
-                        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                        for (int off = 16; off > 0; off >>= 1) {
+                            const float od = __shfl_xor_sync(0xFFFFFFFFu, bd, off);
+                            const uint32_t oj = __shfl_xor_sync(0xFFFFFFFFu, bj, off);
+                            if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                        }
+                        d0nan = __shfl_sync(0xFFFFFFFFu, d0nan ? 1 : 0, 0) != 0;
+                        if (lane == L) best = d0nan ? 0u : bj;  // vector.rs:354-361: a NaN at index 0 is never replaced
                     }
-                    d0nan = __shfl_sync(0xFFFFFFFFu, d0nan ? 1 : 0, 0) != 0;
-                    if (lane == L) best = d0nan ? 0u : bj;  // vector.rs:354-361: a NaN at index 0 is never replaced
                 }
                 if (live) {
                     if (p.codes) store_code(p.codes, p.code_bytes, (size_t)row * p.stride_row + (size_t)s * p.stride_sub, best);
