@@ -46,9 +46,10 @@ def parse():
     p.add_argument("--rows", type=int, default=N_ROWS, help="vectors per GPU per step")
     p.add_argument("--metric", default=ENC_METRIC)
     p.add_argument("--assign", default="auto", choices=["auto", "exact", "tensor"])
-    p.add_argument("--kmeans-iters", type=int, default=5, help="timed k-means iterations (0 = skip)")
+    p.add_argument("--kmeans-iters", type=int, default=25, help="iterations of the timed k-means training call (0 = skip)")
     p.add_argument("--cpu-sample", type=int, default=60_000, help="vectors in the cpu_baseline sample (0 = skip)")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-paths", action="store_true", help="skip the per-path throughputs (BQ/SQ, Manhattan, L2 kinds, TSVQ)")
     return p.parse_args()
 
 
@@ -131,6 +132,98 @@ def cpu_encode_rate(rows, metric, threads=None):
     kind = "port"  # restated Rust loop; the distance kernels are the reference's own hsdlib when sem == hsdlib
     backend = orc.hsd.backend() if orc.hsd is not None else "restated AVX-512 path"
     return rows / dt / 1e6, threads, kind, dt, f"hsdlib: {backend}"
+
+
+def measure_paths(eng, ext, x, pq, peaks):
+    """Device-resident throughput of the remaining hot-path rows on one GPU: CUDA events on the
+    engine stream, 2 warm-up + 5 timed passes each, inputs larger than L2.  Algorithmic bytes/ops per SURVEY 8(d)."""
+    import ctypes as C
+    import torch
+    import vq_b200 as vq
+    lib = eng.lib
+    hbm = peaks["hbm_gbs"]
+    res = {}
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            fn()
+        e1.record(ext)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    def hbm_entry(name, seconds, nbytes, unit_count, unit):
+        gbs = nbytes / seconds / 1e9
+        res[name] = {"value": unit_count / seconds / 1e6, "unit": unit, "ms": seconds * 1e3,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}}
+
+    rows, dim = x.shape
+    # C2: BQ / SQ(8-bit) over 1536-d f32 embeddings, one 2M-row device-resident chunk (12.3 GB in, 3.1 GB out)
+    n2, d2 = 2_000_000, 1536
+    g = torch.Generator(device="cuda"); g.manual_seed(777)
+    e = torch.empty(n2, d2, device="cuda")
+    for r0 in range(0, n2, 250_000):
+        e[r0:r0 + 250_000].normal_(0.0, 0.5, generator=g)
+    q = torch.empty(n2, d2, dtype=torch.uint8, device="cuda")
+    ne = n2 * d2
+    t = timed(lambda: eng.check(lib.vqb_bq_quantize(eng.h, e.data_ptr(), ne, 0.0, 0, 1, q.data_ptr())))
+    hbm_entry("bq_quantize_1536d", t, ne * 5, n2, "Mvec/s")
+    step = np.float32(2.0) / np.float32(255.0)
+    t = timed(lambda: eng.check(lib.vqb_sq_quantize(eng.h, e.data_ptr(), ne, -1.0, 1.0, float(step), 256, q.data_ptr())))
+    hbm_entry("sq8_quantize_1536d", t, ne * 5, n2, "Mvec/s")
+    t = timed(lambda: eng.check(lib.vqb_sq_dequantize(eng.h, q.data_ptr(), ne, -1.0, float(step), e.data_ptr())))
+    hbm_entry("sq8_dequantize_1536d", t, ne * 5, n2, "Mvec/s")
+    del q
+
+    # C4: TSVQ depth-8 build + encode on 1M x 1536 (Euclidean); e now holds SQ-dequantised N(0, 0.5) values
+    n4 = 1_000_000
+    e.normal_(0.0, 0.5, generator=g)
+    x4 = e[:n4]
+    hs = []
+
+    def build():
+        h = C.c_void_p()
+        eng.check(lib.vqb_tsvq_train(eng.h, x4.data_ptr(), n4, d2, 8, 1, C.byref(h)))
+        hs.append(h)
+    t = timed(build, reps=2, warm=1)
+    hbm_entry("tsvq_build_depth8_1Mx1536", t, (2 * 8 + 1) * n4 * d2 * 4, n4, "Mvec/s")
+    tree = hs[-1]
+    for h in hs[:-1]:
+        lib.vqb_tsvq_destroy(h)
+    r4 = torch.empty(n4, d2, dtype=torch.float16, device="cuda")
+    t = timed(lambda: eng.check(lib.vqb_tsvq_encode(tree, x4.data_ptr(), n4, None, r4.data_ptr())))
+    hbm_entry("tsvq_encode_depth8_1Mx1536", t, n4 * d2 * 6, n4, "Mvec/s")
+    lib.vqb_tsvq_destroy(tree)
+    del r4, e, x4
+
+    # PQ encode with the other metrics on the bench batch (same codebooks); Manhattan = C5b's kernel
+    cb = pq.codebooks
+    codes = torch.empty(rows, M, dtype=torch.uint8, device="cuda")
+    for name, metric in (("pq_encode_sqeuclidean", "squared_euclidean"), ("pq_encode_euclidean", "euclidean"),
+                         ("pq_encode_manhattan", "manhattan")):
+        q2 = vq.ProductQuantizer.from_codebooks(cb, vq.Distance(metric), engine=eng)
+        t = timed(lambda: eng.check(lib.vqb_pq_encode(q2._handle, x.data_ptr(), rows, 0, codes.data_ptr(), 1, None)),
+                  reps=3, warm=1)
+        ent = {"value": rows / t / 1e6, "unit": "Mvec/s", "ms": t * 1e3}
+        if metric == "manhattan":   # SURVEY 8d: 2*n*dim*k FP32 CUDA-core ops vs the non-FMA FP32 issue peak
+            ops = 2.0 * rows * dim * K
+            peak = 148 * 128 * 1.965e9 / 1e12   # lanes x SM clock: one non-FMA FP32 op per lane per cycle
+            ent["roofline"] = {"bound": "fp32-issue", "achieved": ops / t / 1e12, "peak": peak, "unit": "Top/s",
+                               "frac": ops / t / 1e12 / peak}
+        else:
+            tf = 2.0 * rows * dim * K / t / 1e12
+            ent["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                               "frac": tf / peaks["bf16_tflops"]}
+        res[name] = ent
+        del q2
+    # PQ decode (codes -> f32 reconstruction): n*m read + n*dim*4 written
+    rec = torch.empty(rows, dim, device="cuda")
+    t = timed(lambda: eng.check(lib.vqb_pq_decode(pq._handle, codes.data_ptr(), 1, rows, rec.data_ptr())))
+    hbm_entry("pq_decode", t, rows * (M + dim * 4), rows, "Mvec/s")
+    return res
 
 
 def run_reference(args, rank, world):
@@ -303,21 +396,42 @@ def main():
             def train(iters):
                 eng.check(eng.lib.vqb_pq_train(eng.h, x.data_ptr(), rows, DIM, M, K, iters, ginit.ctypes.data,
                                                C.byref(opts), cb.ctypes.data, it_run.ctypes.data))
-            train(1)
-            barrier()
-            t0 = time.perf_counter(); train(1); torch.cuda.synchronize(); t_one = time.perf_counter() - t0
-            barrier()
-            t0 = time.perf_counter(); train(1 + args.kmeans_iters); torch.cuda.synchronize()
-            t_many = time.perf_counter() - t0
-            per_iter = (t_many - t_one) / args.kmeans_iters   # removes set-up (allocation, init gather)
+            full_iters = args.kmeans_iters
+            iter_ms = (C.c_float * full_iters)()
+            opts.iter_ms = C.cast(iter_ms, C.POINTER(C.c_float))
+
+            def wall(iters):
+                barrier()
+                t0 = time.perf_counter(); train(iters); torch.cuda.synchronize()
+                return time.perf_counter() - t0
+            wall(2)                                        # warm: allocator, kernels resident
+            # one 25-iteration training call (BASELINE metric): wall time with set-up, and the device time of
+            # every iteration from CUDA events on the engine stream (vqb_train_opts.iter_ms)
+            t_full, per_iter = None, None
+            for _ in range(2):
+                t = wall(full_iters)
+                if t_full is None or t < t_full:
+                    t_full, ran = t, int(it_run.min())
+                    per_iter = statistics.median(list(iter_ms)[:max(1, ran)]) * 1e-3
             if dist_on:
-                t = torch.tensor([per_iter], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX); per_iter = float(t.item())
-            out["kmeans"] = {"value": 1.0 / per_iter, "unit": "iter/s", "ms_per_iter": per_iter * 1e3,
-                             "rows_total": world * rows, "iters_timed": args.kmeans_iters,
-                             "iters_run_min": int(it_run.min()), "update": "fast",
-                             "note": "all 96 subspaces advance per iteration; rows sharded, one fused all-reduce/iter"}
+                t = torch.tensor([per_iter, t_full], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX)
+                per_iter, t_full = float(t[0].item()), float(t[1].item())
+            out["kmeans"] = {"value": ran / t_full, "unit": "iter/s", "ms_per_iter": per_iter * 1e3,
+                             "train_call_ms": t_full * 1e3, "iters_requested": full_iters, "iters_run_min": ran,
+                             "rows_total": world * rows, "iters_timed": ran, "update": "fast",
+                             "note": "value = iterations run / wall time of ONE vqb_pq_train call (25 iterations requested, "
+                                     "workspace set-up and the one-time subspace-major copy included); ms_per_iter = marginal "
+                                     "cost from the difference of two calls; all 96 subspaces advance per iteration; rows "
+                                     "sharded, one fused all-reduce per iteration"}
         except Exception as ex:
             out["kmeans"] = {"value": None, "unit": "iter/s", "error": repr(ex)[:200]}
+
+    # ---- every other path of SURVEY 8(a) at 1 GPU, each against the roofline that bounds it ----
+    if world == 1 and not args.no_paths:
+        try:
+            out["paths"] = measure_paths(eng, ext, x, pq, peaks)
+        except Exception as ex:
+            out["paths"] = {"error": repr(ex)[:300]}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample) ----
     if rank == 0 and world == 1 and args.cpu_sample > 0:

@@ -136,6 +136,9 @@ typedef struct vqb_train_opts {
     void* allreduce_user;
     uint64_t row_offset;         /* global id of this rank's first row (0 on a single GPU) */
     uint64_t n_global;           /* total rows over all ranks (0: == n) */
+    float* iter_ms;              /* diagnostics, may be NULL: host array of max_iters floats; iter_ms[t] receives the
+                                    device time of iteration t in ms (CUDA events on the context stream, the
+                                    all-reduce included), entries of iterations that did not run are left alone */
 } vqb_train_opts;
 
 /* ProductQuantizer::new (src/pq.rs:83-141) == m x lbg_quantize (src/core/vector.rs:390-461).

@@ -64,6 +64,31 @@ def test_bq_sq_bit_exact(vq, oracle, n):
         assert np.array_equal(bits(sq.dequantize(q)), bits(oracle.sq_dequantize(q, mn, mx, lv)))
 
 
+def test_sq_division_on_rounding_boundaries(vq, oracle):
+    """The SQ kernel divides by `step` with a reciprocal + two residual corrections instead of the generic
+    IEEE sequence; it must still be the correctly rounded quotient (sq.rs:125).  Stress it where a wrong last
+    bit changes the code: numerators a few ulps around (j + 0.5) * step, steps with awkward mantissas
+    (all ones, just above a power of two), tiny / huge ranges that take the generic path."""
+    rng = np.random.default_rng(99)
+    cases = [(-1.0, 1.0, 256), (0.0, 1.0, 255), (0.0, 0.99999994, 2), (0.0, 1.0000001, 2), (-0.33333334, 0.6666667, 4),
+             (0.0, 3.0, 256), (-7.0, 9.0, 255), (0.0, 1e-30, 17), (-1e25, 1e25, 256), (1.0, 1.0000038, 33),
+             (0.0, 16777215.0, 256), (-123.456, 789.012, 200)]
+    for mn, mx, lv in cases:
+        mn, mx = F(mn), F(mx)
+        step = oracle.sq_step(float(mn), float(mx), lv)
+        j = rng.integers(0, lv, 400_000).astype(F)
+        base = (mn + (j + F(0.5)) * F(step)).astype(F)
+        x = base.copy()
+        for k in range(1, 5):   # +-1..4 ulps around each half-way point
+            x = np.concatenate([x, np.nextafter(x[-base.size:], F(np.inf)), ])
+        lo = base.copy()
+        for k in range(4):
+            lo = np.nextafter(lo, F(-np.inf)); x = np.concatenate([x, lo])
+        x = np.concatenate([x, rng.uniform(float(mn), float(mx), 400_000).astype(F)])
+        sq = vq.ScalarQuantizer(float(mn), float(mx), lv)
+        assert np.array_equal(sq.quantize(x), oracle.sq_quantize(x, float(mn), float(mx), lv)), (mn, mx, lv)
+
+
 def test_bq_sq_unaligned_and_kats(vq, oracle):
     x = (np.random.default_rng(1).standard_normal(10_001)).astype(F)[1:]  # 4-byte aligned only
     assert np.array_equal(vq.BinaryQuantizer(0.1).quantize(x), oracle.bq_quantize(x, 0.1, 0, 1))

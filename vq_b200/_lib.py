@@ -29,6 +29,7 @@ class TrainOpts(C.Structure):
         ("reseed", RESEED_FN), ("reseed_user", C.c_void_p),
         ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p),
         ("row_offset", C.c_uint64), ("n_global", C.c_uint64),
+        ("iter_ms", C.POINTER(C.c_float)),
     ]
 
 

@@ -28,7 +28,26 @@ struct vqb_ctx {
     // pinned mailbox for small per-iteration read-backs
     void* mailbox = nullptr;
     size_t mailbox_bytes = 0;
+    // grow-only device staging for host-pointer calls (double-buffered x / codes / f16 chunks) and the
+    // events that order the three streams: kept across calls so a call costs no cudaMalloc / cudaFree
+    void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t stage_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+// Returns ctx->stage[i] grown to at least `bytes` (callers hold ctx->mu; previous users of the slot are
+// complete because every host-pointer call synchronises its streams before returning).
+inline cudaError_t vqb_stage(vqb_ctx* ctx, int i, size_t bytes, void** out) {
+    if (ctx->stage_bytes[i] < bytes) {
+        if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        ctx->stage[i] = nullptr; ctx->stage_bytes[i] = 0;
+        cudaError_t e = cudaMalloc(&ctx->stage[i], bytes);
+        if (e != cudaSuccess) return e;
+        ctx->stage_bytes[i] = bytes;
+    }
+    *out = ctx->stage[i];
+    return cudaSuccess;
+}
 
 inline int vqb_fail(vqb_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];

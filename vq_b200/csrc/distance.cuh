@@ -246,6 +246,9 @@ VQB_DEV float vq_distance(int metric, const A& a, const B& b, int n) {
         if (!ok) s = dist2_seq<N>(a, b, n);  // distance.rs:75-83 has the same order as distance2
         return metric == 1 ? __fsqrt_rn(s) : s;
     } else if (metric == 2) {
+        // n < 16: hsdlib's kernel is its scalar tail only (manhattan.c:132-163), i.e. the same sequential sum as
+        // the Rust fallback it defers to on NaN/Inf -- one formula for every input, no per-element checks
+        if (N > 0 && N < 16) return rust_l1<N>(a, b, n);
         float s = hsd_manhattan<N>(a, b, n, ok);
         return ok ? s : rust_l1<N>(a, b, n);
     } else {

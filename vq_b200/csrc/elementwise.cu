@@ -24,11 +24,26 @@ struct BqQ {
 };
 struct SqQ {
     float mn, mx, step; uint32_t top;  // top = levels - 1
+    float rinv;                        // RN(1 / step), or 0 when the fast division below is not applicable
+    // Correctly rounded a / step without the generic division sequence: q0 = RN(a * rinv) is within 2 ulp,
+    // one residual correction makes it faithful, a second one (Markstein: y = RN(1/b), q faithful,
+    // r = a - b*q exact => RN(q + r*y) = RN(a/b)) makes it the IEEE quotient.  The residuals are exact only
+    // away from underflow/overflow, so tiny, huge and non-finite numerators take __fdiv_rn.
+    __device__ __forceinline__ float div_step(float a) const {
+        if (rinv != 0.0f && ((a >= 1e-18f && a <= 1e18f) || a == 0.0f)) {
+            float q = __fmul_rn(a, rinv);
+            float r = __fmaf_rn(-q, step, a);
+            q = __fmaf_rn(r, rinv, q);
+            r = __fmaf_rn(-q, step, a);
+            return __fmaf_rn(r, rinv, q);
+        }
+        return __fdiv_rn(a, step);
+    }
     __device__ __forceinline__ uint8_t operator()(float x) const {
         float c = x;                    // f32::clamp: NaN falls through both tests (sq.rs:124)
         if (c < mn) c = mn;
         if (c > mx) c = mx;
-        float q = roundf(__fdiv_rn(__fsub_rn(c, mn), step));  // f32::round: half away from zero
+        float q = roundf(div_step(__fsub_rn(c, mn)));  // f32::round: half away from zero
         uint32_t idx = __float2uint_rz(q);                    // `as usize`: saturating, NaN -> 0
         return (uint8_t)min(idx, top);                        // sq.rs:126
     }
@@ -199,7 +214,9 @@ int vqb_sq_quantize(vqb_ctx* ctx, const float* x, size_t n, float mn, float mx, 
                     uint8_t* out) {
     if (!ctx) return VQB_ERR_NULL_PTR;
     if (levels < 2 || levels > 256) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "levels must be in [2,256]");
-    return run_f32_to_u8(ctx, x, n, out, SqQ{mn, mx, step, levels - 1});
+    // fast exact division only for steps whose reciprocal and residual products stay in the normal range
+    const float rinv = (step >= 1e-18f && step <= 1e18f) ? 1.0f / step : 0.0f;
+    return run_f32_to_u8(ctx, x, n, out, SqQ{mn, mx, step, levels - 1, rinv});
 }
 
 int vqb_sq_dequantize(vqb_ctx* ctx, const uint8_t* codes, size_t n, float mn, float step, float* out) {

@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 struct vqb_pq {
     vqb_ctx* ctx = nullptr;
@@ -38,11 +39,35 @@ __global__ void k_pq_decode(const void* __restrict__ codes, uint32_t code_bytes,
     out[t] = __half2float(__float2half_rn(cb[((size_t)s * k + c) * d + comp]));
 }
 
-struct Event {
-    cudaEvent_t e = nullptr;
-    ~Event() { if (e) cudaEventDestroy(e); }
-    cudaError_t make() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+// non-owning views of the staging buffers / events cached in the context
+// decode, vector form for sub_dim % 4 == 0: thread = (row, subspace) writes its d floats as float4s; the
+// codebook (m*k*d*4 bytes, L1/L2 resident) is read through the read-only path, the output is streamed
+template <int CB>
+__global__ void __launch_bounds__(256) k_pq_decode_v4(const void* __restrict__ codes, size_t n, int m, int k, int d,
+                                                      const float* __restrict__ cb, float* __restrict__ out) {
+    const size_t total = n * (size_t)m;
+    for (size_t rs = (size_t)blockIdx.x * blockDim.x + threadIdx.x; rs < total; rs += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(rs % m);
+        uint32_t c = CB == 1 ? static_cast<const uint8_t*>(codes)[rs]
+                   : CB == 2 ? static_cast<const uint16_t*>(codes)[rs]
+                             : static_cast<const uint32_t*>(codes)[rs];
+        if (c >= (uint32_t)k) c = (uint32_t)k - 1;  // defensive: never read outside the codebook
+        const float4* src = reinterpret_cast<const float4*>(cb + ((size_t)s * k + c) * d);
+        float4* dst = reinterpret_cast<float4*>(out + rs * d);
+        for (int q = 0; q < d / 4; ++q) {
+            float4 v = __ldg(src + q);
+            v.x = __half2float(__float2half_rn(v.x)); v.y = __half2float(__float2half_rn(v.y));
+            v.z = __half2float(__float2half_rn(v.z)); v.w = __half2float(__float2half_rn(v.w));
+            __stcs(dst + q, v);
+        }
+    }
+}
+
+struct Buf {
+    void* p = nullptr;
+    template <typename T> T* as() const { return static_cast<T*>(p); }
 };
+struct Ev { cudaEvent_t e = nullptr; };
 
 int encode_device(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, void* codes, uint32_t code_bytes,
                   __half* recon, cudaStream_t stream_override = nullptr) {
@@ -137,19 +162,22 @@ int vqb_pq_encode(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, vo
     if (x_dev && c_dev && r_dev)  // all on device: one asynchronous launch
         return encode_device(pq, x, n, assign_mode, codes_out, code_bytes, reinterpret_cast<__half*>(recon_out));
 
-    // ---- chunked three-stream pipeline ----
-    size_t chunk_rows = std::max<size_t>(1, (size_t(128) << 20) / (dim * sizeof(float)));
+    // ---- chunked three-stream pipeline (staging buffers and events live in the context) ----
+    static const size_t chunk_mb = [] { const char* e = std::getenv("VQB_CHUNK_MB"); long v = e ? std::atol(e) : 0; return (size_t)(v > 0 ? v : 64); }();
+    size_t chunk_rows = std::max<size_t>(1, (chunk_mb << 20) / (dim * sizeof(float)));
     chunk_rows = std::min(chunk_rows, n);
-    DevBuf xin[2], cst[2], rst[2];
-    Event ev_in[2], ev_comp[2], ev_out[2];
+    Buf xin[2], cst[2], rst[2];
+    Ev ev_in[2], ev_comp[2], ev_out[2], ev_start;
+    for (int i = 0; i < 7; ++i)
+        if (!ctx->stage_ev[i]) VQB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) {
-        if (!x_dev) VQB_CUDA(ctx, xin[b].alloc(chunk_rows * dim * 4));
-        if (codes_out && !c_dev) VQB_CUDA(ctx, cst[b].alloc(chunk_rows * pq->m * code_bytes));
-        if (recon_out && !r_dev) VQB_CUDA(ctx, rst[b].alloc(chunk_rows * dim * 2));
-        VQB_CUDA(ctx, ev_in[b].make()); VQB_CUDA(ctx, ev_comp[b].make()); VQB_CUDA(ctx, ev_out[b].make());
+        if (!x_dev) VQB_CUDA(ctx, vqb_stage(ctx, b, chunk_rows * dim * 4, &xin[b].p));
+        if (codes_out && !c_dev) VQB_CUDA(ctx, vqb_stage(ctx, 2 + b, chunk_rows * pq->m * code_bytes, &cst[b].p));
+        if (recon_out && !r_dev) VQB_CUDA(ctx, vqb_stage(ctx, 4 + b, chunk_rows * dim * 2, &rst[b].p));
+        ev_in[b].e = ctx->stage_ev[b]; ev_comp[b].e = ctx->stage_ev[2 + b]; ev_out[b].e = ctx->stage_ev[4 + b];
     }
     // order the pipeline after whatever is already queued on the context stream
-    Event ev_start; VQB_CUDA(ctx, ev_start.make());
+    ev_start.e = ctx->stage_ev[6];
     VQB_CUDA(ctx, cudaEventRecord(ev_start.e, ctx->stream));
     VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_start.e, 0));
     size_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
@@ -196,9 +224,17 @@ int vqb_pq_decode(vqb_pq* pq, const void* codes, uint32_t code_bytes, size_t n, 
     InputView in; OutputView ov;
     VQB_TRY(in.bind(ctx, codes, n * pq->m * code_bytes));
     VQB_TRY(ov.bind(ctx, out, n * dim * 4));
-    k_pq_decode<<<cdiv(n * dim, 256), 256, 0, ctx->stream>>>(in.dev, code_bytes, n, (int)pq->m, (int)pq->k,
-                                                            (int)pq->d, pq->cb.as<float>(),
-                                                            static_cast<float*>(ov.dev));
+    if (pq->d % 4 == 0 && (reinterpret_cast<uintptr_t>(ov.dev) & 15) == 0) {
+        const unsigned grid = (unsigned)std::min<size_t>(cdiv(n * pq->m, 256), (size_t)ctx->sm_count * 32);
+        float* o = static_cast<float*>(ov.dev);
+        if (code_bytes == 1) k_pq_decode_v4<1><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
+        else if (code_bytes == 2) k_pq_decode_v4<2><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
+        else k_pq_decode_v4<4><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
+    } else {
+        k_pq_decode<<<cdiv(n * dim, 256), 256, 0, ctx->stream>>>(in.dev, code_bytes, n, (int)pq->m, (int)pq->k,
+                                                                (int)pq->d, pq->cb.as<float>(),
+                                                                static_cast<float*>(ov.dev));
+    }
     VQB_LAUNCHED(ctx);
     VQB_TRY(ov.finish(ctx));
     if (in.was_host || ov.host) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -44,6 +44,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -125,7 +126,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 // waiting roles that are not on the critical path: poll, then sleep between polls
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
     uint32_t ok = 0;
     for (;;) {
         asm volatile(
@@ -136,7 +137,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) break;
-        __nanosleep(64);
+        __nanosleep(sleep_ns);
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -350,6 +351,7 @@ struct TcParams {
     float* dbg_scores;            // DEBUG kernels only: [n][256] raw tensor-core scores of subspace dbg_sub
     unsigned long long* dbg_stats;  // DEBUG kernels only: [0] (row, subspace) pairs resolved by the full re-scan
     int dbg_sub;
+    uint32_t sleep_ns;            // back-off between polls of the roles that run ahead of / behind the critical path
 };
 
 __device__ __forceinline__ void store_code(void* codes, uint32_t code_bytes, size_t off, uint32_t v) {
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
             if (lane == 0) {
                 for (int it = 0; it < my_tiles; ++it) {
                     const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-                    mbar_wait_relaxed(RAW_EMPTY(st), ph ^ 1);
+                    mbar_wait_relaxed(RAW_EMPTY(st), ph ^ 1, p.sleep_ns);
                     mbar_expect_tx(RAW_FULL(st), RAW_BYTES);
                     const int tile = part + it * p.parts;
                     tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-            mbar_wait_relaxed(RAW_FULL(st), ph);
+            mbar_wait_relaxed(RAW_FULL(st), ph, p.sleep_ns);
             const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
             for (int i = 0; i < g_cnt; ++i) {
                 if (!(act_mask >> i & 1)) continue;
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 l1.y = v1.y - __uint_as_float(__float_as_uint(v1.y) & 0xFFFFE000u);
                 l1.z = v1.z - __uint_as_float(__float_as_uint(v1.z) & 0xFFFFE000u);
                 l1.w = v1.w - __uint_as_float(__float_as_uint(v1.w) & 0xFFFFE000u);
-                mbar_wait_relaxed(A_EMPTY(ast), aph ^ 1);
+                mbar_wait_relaxed(A_EMPTY(ast), aph ^ 1, p.sleep_ns);
                 float4* dst = reinterpret_cast<float4*>(sm + OFF_AP + ast * AP_BYTES + (r >> 3) * 256 + (r & 7) * 16);
                 dst[0] = l0; dst[8] = l1;
                 fence_proxy_async();
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 const uint32_t sexp = (__float_as_uint(S) >> 23) & 0xFFu;
                 const float H = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
                 const float M = amb ? -1.0f : KAPPA * S;
-                mbar_wait_relaxed(MG_EMPTY(mg), mph ^ 1);
+                mbar_wait_relaxed(MG_EMPTY(mg), mph ^ 1, p.sleep_ns);
                 reinterpret_cast<float2*>(sm + OFF_MG + mg * MG_BYTES)[r] = make_float2(H, M);
                 mbar_arrive(MG_FULL(mg));
                 ++u;
@@ -660,12 +662,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
                 const int s = s0 + i;
-                if (!raw_seen) { mbar_wait_relaxed(RAW_FULL(st), ph); raw_seen = true; }
+                if (!raw_seen) { mbar_wait_relaxed(RAW_FULL(st), ph, p.sleep_ns); raw_seen = true; }
                 // this row's sub-vector, halves in this lane's gather order
                 const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
                 const float4 xa = *reinterpret_cast<const float4*>(rawrow + (((2 * i + h0) ^ (r & 7)) << 4));
                 const float4 xb = *reinterpret_cast<const float4*>(rawrow + (((2 * i + (h0 ^ 1)) ^ (r & 7)) << 4));
-                mbar_wait_relaxed(RES_FULL(rs), rph);
+                mbar_wait_relaxed(RES_FULL(rs), rph, p.sleep_ns);
                 const float2 rv = reinterpret_cast<const float2*>(sm + OFF_RES + rs * RES_BYTES)[r];
                 mbar_arrive(RES_EMPTY(rs));
                 const uint32_t word = __float_as_uint(rv.y);
@@ -844,6 +846,8 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
     p.parts = std::max(1, std::min(p.num_tiles, ctx->sm_count / p.n_groups));
     p.code_bytes = code_bytes;
     p.dbg_scores = dbg_scores; p.dbg_stats = dbg_stats; p.dbg_sub = dbg_sub;
+    static const uint32_t sleep_ns = [] { const char* e = std::getenv("VQB_TC_SLEEP_NS"); long v = e ? std::atol(e) : -1; return (uint32_t)(v >= 0 ? v : 256); }();
+    p.sleep_ns = sleep_ns;
     const int grid = p.n_groups * p.parts;
     if (dbg_scores || dbg_stats) {
         if (mk == MK_COSINE) return launch_tc<MK_COSINE, true>(ctx, map, p, grid);

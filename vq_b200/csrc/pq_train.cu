@@ -35,7 +35,7 @@ inline double now_ms() {
 }
 
 constexpr int RX_THREADS = 256;   // one radix step = 256 consecutive rows
-constexpr int RX_STEPS = 8;       // steps per chunk
+constexpr int RX_STEPS = 32;      // steps per chunk: (chunk, bin) runs of ~32 ids = 128 B keep the scatter's writes line-sized
 constexpr int RX_CHUNK = RX_THREADS * RX_STEPS;
 constexpr int RX_WARPS = RX_THREADS / 32;
 
@@ -156,7 +156,7 @@ __global__ void k_cluster_ranges(const void* __restrict__ codes, uint32_t code_b
 // thread = (active pos, cluster j, segment, component).  segs == 1 reproduces the reference's
 // summation order exactly; segs > 1 splits each member list into equal contiguous pieces.
 __global__ void __launch_bounds__(256)
-k_chain_sums(const float* __restrict__ x, size_t n, int dim, int d, int k, int segs,
+k_chain_sums(const float* __restrict__ x, size_t n, size_t row_stride, size_t sub_stride, int d, int k, int segs,
              const int* __restrict__ sub_list, int n_active, const uint32_t* __restrict__ ids,
              const uint32_t* __restrict__ seg_beg, const uint32_t* __restrict__ seg_end,
              float* __restrict__ partial /* [m][k][segs][d] */) {
@@ -172,17 +172,20 @@ k_chain_sums(const float* __restrict__ x, size_t n, int dim, int d, int k, int s
     uint32_t b = off + (uint32_t)(((uint64_t)cnt * seg) / segs);
     uint32_t e = off + (uint32_t)(((uint64_t)cnt * (seg + 1)) / segs);
     const uint32_t* idp = ids + s * n;
-    const float* xs = x + s * d + comp;
+    // x is either the caller's row-major matrix (row_stride = dim, sub_stride = d) or the subspace-major
+    // copy [m][n][d] (row_stride = d, sub_stride = n*d): the latter keeps the rows of one subspace adjacent,
+    // so the member gathers of neighbouring chains land in the same DRAM pages / L2 lines
+    const float* xs = x + s * sub_stride + comp;
     float acc = 0.0f;
     uint32_t i = b;
     for (; i + 8 <= e; i += 8) {
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(xs + (size_t)__ldg(idp + i + u) * dim);
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(xs + (size_t)__ldg(idp + i + u) * row_stride);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
     }
-    for (; i < e; ++i) acc = __fadd_rn(acc, __ldg(xs + (size_t)__ldg(idp + i) * dim));
+    for (; i < e; ++i) acc = __fadd_rn(acc, __ldg(xs + (size_t)__ldg(idp + i) * row_stride));
     partial[((s * k + j) * segs + seg) * d + comp] = acc;
 }
 
@@ -250,12 +253,32 @@ __global__ void k_scatter_subvecs(const float* __restrict__ src, int d, const lo
     codebooks[(size_t)dst_idx[e] * d + comp] = src[t];
 }
 
+// One-time subspace-major copy xt[s][row][0..d) = x[row][s*d..] for the update's member gathers.
+// A warp takes 32 consecutive rows of one subspace: its writes are one contiguous run, its reads are
+// full 32-byte sectors; the other warps of the block read the neighbouring subspaces of the same rows.
+__global__ void __launch_bounds__(256)
+k_subspace_major(const float* __restrict__ x, size_t n, int dim, int d, int m, float* __restrict__ xt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t row = (size_t)blockIdx.x * 32 + lane;
+    if (row >= n) return;
+    for (int s = warp; s < m; s += 8) {
+        const float* src = x + row * dim + (size_t)s * d;
+        float* dst = xt + ((size_t)s * n + row) * d;
+        if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+            for (int c = 0; c < d; c += 4) *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+        } else {
+            for (int c = 0; c < d; ++c) dst[c] = __ldg(src + c);
+        }
+    }
+}
+
 struct TrainWs {
     size_t n = 0, dim = 0, m = 0, k = 0, d = 0;
     uint32_t code_bytes = 1;
     int n_chunks = 0, segs = 1, passes = 1;
     DevBuf codes, ids_a, ids_b, chunk_hist, bin_off, seg_beg, seg_end, partial, pack, cb;
     DevBuf sub_list, is_active, changed, counts, g_rows, g_subs, g_dst, g_vals, tc_prep;
+    DevBuf xt;  // optional subspace-major copy of x (see k_subspace_major); absent when memory is short
     int alloc(vqb_ctx* ctx, size_t n_, size_t dim_, size_t m_, size_t k_, int segs_) {
         n = n_; dim = dim_; m = m_; k = k_; d = dim / m; segs = segs_;
         code_bytes = k <= 256 ? 1 : (k <= 65536 ? 2 : 4);
@@ -375,7 +398,9 @@ int train_iteration(vqb_ctx* ctx, TrainWs& ws, const TrainArgs& a, const std::ve
 
     // sum
     size_t chains = (size_t)na * k * ws.segs * d;
-    k_chain_sums<<<cdiv(chains, 256), 256, 0, ctx->stream>>>(a.x, n, (int)a.dim, (int)d, (int)k, ws.segs, sl, na,
+    const bool use_xt = ws.xt.p != nullptr;
+    k_chain_sums<<<cdiv(chains, 256), 256, 0, ctx->stream>>>(use_xt ? ws.xt.as<float>() : a.x, n, use_xt ? d : a.dim,
+                                                            use_xt ? n * d : d, (int)d, (int)k, ws.segs, sl, na,
                                                             sorted, ws.seg_beg.as<uint32_t>(),
                                                             ws.seg_end.as<uint32_t>(), ws.partial.as<float>());
     VQB_LAUNCHED(ctx);
@@ -473,6 +498,18 @@ int vqb_pq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, s
     if (trace_on()) std::fprintf(stderr, "[vqb trace] bind + workspace alloc: %.3f ms\n", now_ms() - t_enter);
     TrainArgs a{static_cast<const float*>(xin.dev), n, dim, m, k, d, o.assign_mode, o.allreduce, o.allreduce_user,
                 o.row_offset};
+    // subspace-major copy for the update's gathers: pays for itself after about two iterations; skipped for
+    // small inputs, single-iteration calls, m == 1 (already contiguous) or when the memory is not there
+    static const bool no_xt = [] { const char* e = std::getenv("VQB_NO_XT"); return e && *e && *e != '0'; }();
+    if (!no_xt && max_iters >= 2 && m > 1 && n >= 65536) {
+        if (ws.xt.alloc(n * dim * sizeof(float)) == cudaSuccess) {
+            k_subspace_major<<<cdiv(n, 32), 256, 0, ctx->stream>>>(a.x, n, (int)dim, (int)d, (int)m, ws.xt.as<float>());
+            VQB_LAUNCHED(ctx);
+        } else {
+            cudaGetLastError();  // not enough memory: gather from the caller's layout instead
+            ws.xt.p = nullptr; ws.xt.bytes = 0;
+        }
+    }
 
     // vector.rs:413: the sampled rows become the initial centroids
     {
@@ -493,13 +530,22 @@ int vqb_pq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, s
     std::vector<int> active(m);
     for (size_t s = 0; s < m; ++s) active[s] = (int)s;
     std::vector<uint32_t> iters(m, 0), h_changed(m), h_counts(m * k);
+    cudaEvent_t ev_it[2] = {nullptr, nullptr};
+    if (o.iter_ms) {
+        VQB_CUDA(ctx, cudaEventCreate(&ev_it[0]));
+        VQB_CUDA(ctx, cudaEventCreate(&ev_it[1]));
+    }
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 2; ++i) if (e[i]) cudaEventDestroy(e[i]); } } ev_guard{ev_it};
     for (size_t it = 0; it < max_iters && !active.empty(); ++it) {
         const double t0 = trace_on() ? now_ms() : 0.0;
+        if (o.iter_ms) VQB_CUDA(ctx, cudaEventRecord(ev_it[0], ctx->stream));
         VQB_TRY(train_iteration(ctx, ws, a, active));
+        if (o.iter_ms) VQB_CUDA(ctx, cudaEventRecord(ev_it[1], ctx->stream));
         const double t1 = trace_on() ? now_ms() : 0.0;
         VQB_CUDA(ctx, cudaMemcpyAsync(h_changed.data(), ws.changed.p, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
         VQB_CUDA(ctx, cudaMemcpyAsync(h_counts.data(), ws.counts.p, m * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
         VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (o.iter_ms) VQB_CUDA(ctx, cudaEventElapsedTime(&o.iter_ms[it], ev_it[0], ev_it[1]));
         if (trace_on())
             std::fprintf(stderr, "[vqb trace] iter %zu: active=%zu enqueue=%.3f ms, wait=%.3f ms\n", it, active.size(),
                          t1 - t0, now_ms() - t1);
