@@ -327,7 +327,8 @@ def test_pq_device_pointer_and_chunked_host_paths_agree(vq):
 
 
 # ------------------------------------------------------------------ TSVQ
-@pytest.mark.parametrize("n,dim,depth", [(3000, 32, 5), (1000, 33, 4), (500, 1536, 3), (257, 8, 8), (64, 4, 10)])
+@pytest.mark.parametrize("n,dim,depth", [(3000, 32, 5), (1000, 33, 4), (500, 1536, 3), (257, 8, 8), (64, 4, 10),
+                                         (6000, 256, 8), (2500, 1536, 5)])  # all three ring configurations of k_colsum_w
 def test_tsvq_build_bit_exact(vq, oracle, n, dim, depth):
     x = mixture(n, dim, 70 + dim, comps=8, sigma=0.5)
     if dim == 8:
@@ -362,7 +363,7 @@ def test_tsvq_reference_cases(vq, oracle):
 
 
 @pytest.mark.parametrize("metric", METRICS)
-@pytest.mark.parametrize("dim", [8, 33, 100, 1536])
+@pytest.mark.parametrize("dim", [8, 33, 100, 128, 1536])
 def test_tsvq_encode_exact(vq, oracle, metric, dim):
     n = 2000 if dim < 1000 else 600
     x = mixture(n, dim, 80, comps=16, sigma=0.5)

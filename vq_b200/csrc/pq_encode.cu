@@ -39,30 +39,29 @@ __global__ void k_pq_decode(const void* __restrict__ codes, uint32_t code_bytes,
     out[t] = __half2float(__float2half_rn(cb[((size_t)s * k + c) * d + comp]));
 }
 
-// non-owning views of the staging buffers / events cached in the context
-// decode, vector form for sub_dim % 4 == 0: thread = (row, subspace) writes its d floats as float4s; the
-// codebook (m*k*d*4 bytes, L1/L2 resident) is read through the read-only path, the output is streamed
+// decode, vector form for sub_dim % 4 == 0: thread = one float4 of the output, so a warp's store covers 512
+// contiguous bytes; the codebook (m*k*d*4 bytes, L1/L2 resident) is read through the read-only path
 template <int CB>
 __global__ void __launch_bounds__(256) k_pq_decode_v4(const void* __restrict__ codes, size_t n, int m, int k, int d,
                                                       const float* __restrict__ cb, float* __restrict__ out) {
-    const size_t total = n * (size_t)m;
-    for (size_t rs = (size_t)blockIdx.x * blockDim.x + threadIdx.x; rs < total; rs += (size_t)gridDim.x * blockDim.x) {
+    const int q4 = d >> 2;                       // float4s per (row, subspace)
+    const size_t total = n * (size_t)m * q4;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t rs = t / q4;
+        const int q = (int)(t - rs * q4);
         const int s = (int)(rs % m);
         uint32_t c = CB == 1 ? static_cast<const uint8_t*>(codes)[rs]
                    : CB == 2 ? static_cast<const uint16_t*>(codes)[rs]
                              : static_cast<const uint32_t*>(codes)[rs];
         if (c >= (uint32_t)k) c = (uint32_t)k - 1;  // defensive: never read outside the codebook
-        const float4* src = reinterpret_cast<const float4*>(cb + ((size_t)s * k + c) * d);
-        float4* dst = reinterpret_cast<float4*>(out + rs * d);
-        for (int q = 0; q < d / 4; ++q) {
-            float4 v = __ldg(src + q);
-            v.x = __half2float(__float2half_rn(v.x)); v.y = __half2float(__float2half_rn(v.y));
-            v.z = __half2float(__float2half_rn(v.z)); v.w = __half2float(__float2half_rn(v.w));
-            __stcs(dst + q, v);
-        }
+        float4 v = __ldg(reinterpret_cast<const float4*>(cb + ((size_t)s * k + c) * d) + q);
+        v.x = __half2float(__float2half_rn(v.x)); v.y = __half2float(__float2half_rn(v.y));
+        v.z = __half2float(__float2half_rn(v.z)); v.w = __half2float(__float2half_rn(v.w));
+        __stcs(reinterpret_cast<float4*>(out) + t, v);
     }
 }
 
+// non-owning views of the staging buffers / events cached in the context
 struct Buf {
     void* p = nullptr;
     template <typename T> T* as() const { return static_cast<T*>(p); }
@@ -225,7 +224,7 @@ int vqb_pq_decode(vqb_pq* pq, const void* codes, uint32_t code_bytes, size_t n, 
     VQB_TRY(in.bind(ctx, codes, n * pq->m * code_bytes));
     VQB_TRY(ov.bind(ctx, out, n * dim * 4));
     if (pq->d % 4 == 0 && (reinterpret_cast<uintptr_t>(ov.dev) & 15) == 0) {
-        const unsigned grid = (unsigned)std::min<size_t>(cdiv(n * pq->m, 256), (size_t)ctx->sm_count * 32);
+        const unsigned grid = (unsigned)std::min<size_t>(cdiv(n * pq->m * (pq->d / 4), 256), (size_t)ctx->sm_count * 64);
         float* o = static_cast<float*>(ov.dev);
         if (code_bytes == 1) k_pq_decode_v4<1><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
         else if (code_bytes == 2) k_pq_decode_v4<2><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 struct vqb_tsvq {
     vqb_ctx* ctx = nullptr;
@@ -120,6 +121,175 @@ k_colsum(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm
     if (tid < ncol) {
         if (MODE == 0) acc = __fdiv_rn(acc, __uint2float_rn(ns.len));  // `vectors.len()` as f32
         out[(size_t)blockIdx.y * dim + col0 + tid] = acc;
+    }
+}
+
+// The same chains, one WARP per (node, 32-column slice) with its own cp.async ring and no block-wide barrier:
+// the sequential f32 chain of a (node, column) pair cannot be split without changing its rounding, so the
+// kernel's speed is rows per cycle per chain.  Here a lane's chain advances one row per LDS + dependent FADD
+// while the warp's next tiles are in flight, and hundreds of independent warps keep HBM busy on the levels that
+// have enough (node, slice) pairs; on the first levels (48, 96, ... chains of 32 columns) the chain itself binds.
+// A warp's bandwidth is (bytes it keeps in flight) / (memory latency), so the ring depth is traded against warps
+// per CTA at a fixed 64 KB: levels with few chains get one warp per CTA and a 16-deep ring (60 KB in flight per
+// chain, CTAs spread over the SMs), levels with thousands of chains get four warps with 4-deep rings.
+constexpr int CW_ROWS = 32;
+constexpr int CW_SMEM = 16 * CW_ROWS * CS_SLICE * 4;  // 64 KB = warps x stages x 4 KB
+
+template <int MODE, int CW_WARPS, int CW_STAGES>
+__global__ void __launch_bounds__(CW_WARPS * 32)
+k_colsum_w(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm, const NodeSeg* __restrict__ nodes,
+           const float* __restrict__ mean, float* __restrict__ out, int n_slices, unsigned total_warps) {
+    extern __shared__ __align__(16) float ring[];  // [warp][stage][row][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned wg = blockIdx.x * CW_WARPS + warp;
+    if (wg >= total_warps) return;
+    const unsigned node = wg / n_slices;
+    const int col0 = (int)(wg % n_slices) * CS_SLICE;
+    const NodeSeg ns = nodes[node];
+    const uint32_t* ids = perm + ns.beg;
+    float* myring = ring + (size_t)warp * CW_STAGES * CW_ROWS * CS_SLICE;
+    const int n_tiles = (int)((ns.len + CW_ROWS - 1) / CW_ROWS);
+    const int sub = lane >> 3, part = (lane & 7) * 4;  // 8 lanes x 16 B cover one 128-byte row slice
+
+    // the row ids of a tile are fetched one call ahead, so no issue() waits on a global load
+    uint32_t idv_next = (lane < (int)min((uint32_t)CW_ROWS, ns.len)) ? __ldg(ids + lane) : 0u;
+    auto issue = [&](int tile) {
+        if (tile < n_tiles) {
+            float* st = myring + (size_t)(tile % CW_STAGES) * CW_ROWS * CS_SLICE;
+            const int r0 = tile * CW_ROWS;
+            const int rows = min(CW_ROWS, (int)ns.len - r0);
+            const uint32_t idv = idv_next;
+            const int rn = r0 + CW_ROWS + lane;
+            idv_next = rn < (int)ns.len ? __ldg(ids + rn) : 0u;
+#pragma unroll
+            for (int p = 0; p < CW_ROWS / 4; ++p) {
+                const int r = p * 4 + sub;
+                const uint32_t id = __shfl_sync(0xFFFFFFFFu, idv, r);
+                if (r < rows) cp_async16(st + r * CS_SLICE + part, x + (size_t)id * dim + col0 + part);
+            }
+        }
+        cp_async_commit();  // one group per call keeps the wait arithmetic uniform
+    };
+
+    float acc = 0.0f, mu = 0.0f;
+    if (MODE == 1) mu = mean[(size_t)node * dim + col0 + lane];
+#pragma unroll
+    for (int s = 0; s < CW_STAGES - 1; ++s) issue(s);
+    for (int t = 0; t < n_tiles; ++t) {
+        issue(t + CW_STAGES - 1);
+        cp_async_wait<CW_STAGES - 1>();
+        __syncwarp();
+        const float* st = myring + (size_t)(t % CW_STAGES) * CW_ROWS * CS_SLICE + lane;
+        const int rows = min(CW_ROWS, (int)ns.len - t * CW_ROWS);
+        if (rows == CW_ROWS) {
+            float v[CW_ROWS];
+#pragma unroll
+            for (int r = 0; r < CW_ROWS; ++r) v[r] = st[r * CS_SLICE];
+#pragma unroll
+            for (int r = 0; r < CW_ROWS; ++r) {
+                if (MODE == 0) acc = __fadd_rn(acc, v[r]);
+                else { const float df = __fsub_rn(v[r], mu); acc = __fadd_rn(acc, __fmul_rn(df, df)); }
+            }
+        } else {
+            for (int r = 0; r < rows; ++r) {
+                const float vv = st[r * CS_SLICE];
+                if (MODE == 0) acc = __fadd_rn(acc, vv);
+                else { const float df = __fsub_rn(vv, mu); acc = __fadd_rn(acc, __fmul_rn(df, df)); }
+            }
+        }
+        __syncwarp();  // every lane is done with this stage before the next issue overwrites it
+    }
+    if (MODE == 0) acc = __fdiv_rn(acc, __uint2float_rn(ns.len));  // `vectors.len()` as f32
+    out[(size_t)node * dim + col0 + lane] = acc;
+}
+
+// Few-chain levels (the first four or five): one CTA per (node, slice) with ONE accumulating warp and SEVEN
+// producer warps.  The chain's dependent FADD (4 cycles a row) is the floor there, so the accumulating warp does
+// nothing else: producers gather the rows with cp.async into a 16-stage ring and publish each tile through a
+// shared-memory sequence word; the consumer publishes its progress so a stage is only overwritten once read.
+constexpr int CP_STAGES = 16, CP_PROD = 7, CP_DEPTH = 2;  // per producer: CP_DEPTH tiles in flight (14 of 16 stages)
+template <int MODE>
+__global__ void __launch_bounds__((CP_PROD + 1) * 32)
+k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm, const NodeSeg* __restrict__ nodes,
+            const float* __restrict__ mean, float* __restrict__ out, int n_slices) {
+    extern __shared__ __align__(16) float ring[];  // [stage][row][32]
+    __shared__ volatile uint32_t full[CP_STAGES];  // tile index + 1 that currently fills the stage
+    __shared__ volatile uint32_t done;             // tiles the consumer has finished
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned node = blockIdx.x / n_slices;
+    const int col0 = (int)(blockIdx.x % n_slices) * CS_SLICE;
+    const NodeSeg ns = nodes[node];
+    const uint32_t* ids = perm + ns.beg;
+    const int n_tiles = (int)((ns.len + CW_ROWS - 1) / CW_ROWS);
+    if (threadIdx.x < CP_STAGES) full[threadIdx.x] = 0;
+    if (threadIdx.x == 0) done = 0;
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---- consumer: the chain
+        float acc = 0.0f, mu = 0.0f;
+        if (MODE == 1) mu = mean[(size_t)node * dim + col0 + lane];
+        for (int t = 0; t < n_tiles; ++t) {
+            const int stg = t % CP_STAGES;
+            while (full[stg] != (uint32_t)(t + 1)) { }
+            __syncwarp();
+            const float* st = ring + (size_t)stg * CW_ROWS * CS_SLICE + lane;
+            const int rows = min(CW_ROWS, (int)ns.len - t * CW_ROWS);
+            if (rows == CW_ROWS) {
+                float v[CW_ROWS];
+#pragma unroll
+                for (int r = 0; r < CW_ROWS; ++r) v[r] = st[r * CS_SLICE];
+#pragma unroll
+                for (int r = 0; r < CW_ROWS; ++r) {
+                    if (MODE == 0) acc = __fadd_rn(acc, v[r]);
+                    else { const float df = __fsub_rn(v[r], mu); acc = __fadd_rn(acc, __fmul_rn(df, df)); }
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const float vv = st[r * CS_SLICE];
+                    if (MODE == 0) acc = __fadd_rn(acc, vv);
+                    else { const float df = __fsub_rn(vv, mu); acc = __fadd_rn(acc, __fmul_rn(df, df)); }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) done = (uint32_t)(t + 1);
+        }
+        if (MODE == 0) acc = __fdiv_rn(acc, __uint2float_rn(ns.len));  // `vectors.len()` as f32
+        out[(size_t)node * dim + col0 + lane] = acc;
+    } else {
+        // ---- producers: tiles p, p + CP_PROD, p + 2 CP_PROD, ...; row ids fetched one tile ahead
+        const int p = warp - 1;
+        const int sub = lane >> 3, part = (lane & 7) * 4;
+        const int my_tiles = (n_tiles - p + CP_PROD - 1) / CP_PROD;
+        auto publish = [&](int i) {  // this producer's i-th tile has landed
+            const int tile = p + i * CP_PROD;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) full[tile % CP_STAGES] = (uint32_t)(tile + 1);
+        };
+        uint32_t idv_next = (p * CW_ROWS + lane < (int)ns.len) ? __ldg(ids + p * CW_ROWS + lane) : 0u;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = p + i * CP_PROD;
+            const int r0 = tile * CW_ROWS;
+            const int rows = min(CW_ROWS, (int)ns.len - r0);
+            const uint32_t idv = idv_next;
+            const long long rn = (long long)r0 + CP_PROD * CW_ROWS + lane;
+            idv_next = rn < (long long)ns.len ? __ldg(ids + rn) : 0u;
+            // the stage's previous tile must have been consumed (plain polling: a measured nanosleep back-off here made
+            // the first levels 15 % slower -- they are bound by how early the gathers are issued, not by the chain)
+            if (tile >= CP_STAGES) while ((int)done < tile - CP_STAGES + 1) { }
+            float* st = ring + (size_t)(tile % CP_STAGES) * CW_ROWS * CS_SLICE;
+#pragma unroll
+            for (int q = 0; q < CW_ROWS / 4; ++q) {
+                const int r = q * 4 + sub;
+                const uint32_t id = __shfl_sync(0xFFFFFFFFu, idv, r);
+                if (r < rows) cp_async16(st + r * CS_SLICE + part, x + (size_t)id * dim + col0 + part);
+            }
+            cp_async_commit();
+            if (i >= CP_DEPTH) { cp_async_wait<CP_DEPTH>(); publish(i - CP_DEPTH); }
+        }
+        cp_async_wait<0>();
+        for (int i = max(0, my_tiles - CP_DEPTH); i < my_tiles; ++i) publish(i);
     }
 }
 
@@ -418,6 +588,69 @@ k_tsvq_encode(const float* __restrict__ x, size_t n, int dim, const float* __res
     }
 }
 
+// Register-resident form for the L2 / L1 metrics when dim is a multiple of 128 (<= 1536): lane (child, j) keeps the
+// vector's elements of AVX lane j (x[j + 16 t]) in registers for the whole descent, so a level costs one centroid
+// load, one subtract and one accumulate per element -- the per-lane order of hsdlib's kernel is unchanged.
+constexpr int TE_MAX_NT = 96;
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+k_tsvq_encode_reg(const float* __restrict__ x, size_t n, int dim, const float* __restrict__ cent,
+                  const int* __restrict__ left, const int* __restrict__ right, uint32_t* __restrict__ leaf_out,
+                  __half* __restrict__ recon) {
+    const size_t row = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= n) return;  // warp-uniform
+    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const int nt = dim >> 4;
+    const float* v = x + row * (size_t)dim;
+    float xr[TE_MAX_NT];
+#pragma unroll
+    for (int t0 = 0; t0 < TE_MAX_NT; t0 += 8)
+        if (t0 < nt) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xr[t0 + u] = __ldg(v + hl + 16 * (t0 + u));
+        }
+    int node = 0;
+    for (;;) {
+        const int l = left[node], r = right[node];
+        if (l >= 0 && r >= 0) {
+            const float* c = cent + (size_t)(half ? r : l) * dim + hl;
+            float acc = 0.f;
+#pragma unroll
+            for (int t0 = 0; t0 < TE_MAX_NT; t0 += 8)
+                if (t0 < nt) {
+                    float cv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) cv[u] = __ldg(c + 16 * (t0 + u));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float df = __fsub_rn(xr[t0 + u], cv[u]);
+                        acc = (METRIC == VQB_MANHATTAN) ? __fadd_rn(acc, fabsf(df)) : __fmaf_rn(df, df, acc);
+                    }
+                }
+            acc = half_reduce16(acc);
+            float dmine = (METRIC == VQB_EUCLIDEAN) ? __fsqrt_rn(acc) : acc;
+            // hsdlib rejects a non-finite result (the Rust side then recomputes sequentially): same route as the generic kernel
+            const bool bad = (hl == 0) && vqb_bad(acc);
+            if (__any_sync(0xFFFFFFFFu, bad)) dmine = pair_distance_halfwarp<METRIC>(v, cent + (size_t)(half ? r : l) * dim, dim, hl);
+            const float dl = __shfl_sync(0xFFFFFFFFu, dmine, 0), dr = __shfl_sync(0xFFFFFFFFu, dmine, 16);
+            node = (dl <= dr) ? l : r;  // tsvq.rs:122
+        } else if (l >= 0) node = l;
+        else if (r >= 0) node = r;
+        else break;
+    }
+    if (leaf_out && lane == 0) leaf_out[row] = (uint32_t)node;
+    if (recon) {  // tsvq.rs:248-254
+        const float4* c4 = reinterpret_cast<const float4*>(cent + (size_t)node * dim);
+        uint2* o = reinterpret_cast<uint2*>(recon + row * (size_t)dim);
+        for (int i = lane; i < dim / 4; i += 32) {
+            const float4 cv = __ldg(c4 + i);
+            __half2 a = __floats2half2_rn(cv.x, cv.y), b = __floats2half2_rn(cv.z, cv.w);
+            uint2 w; w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b);
+            o[i] = w;
+        }
+    }
+}
+
 struct LevelNode { uint32_t id, beg, len, depth_left; };
 
 }  // namespace
@@ -508,6 +741,19 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     const int vec_ok = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(xd) & 15) == 0);
     VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
     VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<0, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<0, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<0, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<1, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<1, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<1, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    const unsigned cta_slots = (unsigned)ctx->sm_count * 3;  // 64 KB CTAs resident at once
+    VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum_pc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
+    VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum_pc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
+    static const bool no_pc = [] { const char* e = std::getenv("VQB_TSVQ_NO_PC"); return e && *e && *e != '0'; }();
+    static const bool old_colsum = [] { const char* e = std::getenv("VQB_TSVQ_OLD_COLSUM"); return e && *e && *e != '0'; }();
+    const bool warp_chains = vec_ok && dim % CS_SLICE == 0 && !old_colsum;  // else: block-wide ring kernel (any dim / alignment)
+    const int n_slices = (int)(dim / CS_SLICE);
 
     DevBuf perm_a, perm_b, vals;
     VQB_CUDA(ctx, perm_a.alloc(n * 4));
@@ -542,6 +788,17 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         VQB_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), ln * sizeof(NodeSeg), cudaMemcpyHostToDevice, st));
         dim3 gcs(cdiv(dim, CS_SLICE), (unsigned)ln);
         if (gcs.y > 65535) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "too many nodes on one level");
+        if (warp_chains) {
+            const unsigned tw = (unsigned)(ln * n_slices);
+            if (tw <= 2 * cta_slots && !no_pc)
+                k_colsum_pc<0><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
+            else if (tw <= cta_slots)
+                k_colsum_w<0, 1, 16><<<tw, 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
+            else if (tw <= 2 * cta_slots)
+                k_colsum_w<0, 2, 8><<<cdiv(tw, 2), 64, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
+            else
+                k_colsum_w<0, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
+        } else
         k_colsum<0><<<gcs, CS_THREADS, CS_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr,
                                                      d_mean.as<float>(), vec_ok);
         VQB_LAUNCHED(ctx);
@@ -590,6 +847,17 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         VQB_CUDA(ctx, cudaMemsetAsync(d_hist.p, 0, sn * 2 * 256 * 4, st));
 
         dim3 gvs(cdiv(dim, CS_SLICE), (unsigned)sn);
+        if (warp_chains) {
+            const unsigned tw = (unsigned)(sn * n_slices);
+            if (tw <= 2 * cta_slots && !no_pc)
+                k_colsum_pc<1><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
+            else if (tw <= cta_slots)
+                k_colsum_w<1, 1, 16><<<tw, 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
+            else if (tw <= 2 * cta_slots)
+                k_colsum_w<1, 2, 8><<<cdiv(tw, 2), 64, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
+            else
+                k_colsum_w<1, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
+        } else
         k_colsum<1><<<gvs, CS_THREADS, CS_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(),
                                                      d_var.as<float>(), vec_ok);
         VQB_LAUNCHED(ctx);
@@ -703,6 +971,18 @@ int vqb_tsvq_encode(vqb_tsvq* t, const float* x, size_t n, uint32_t* leaf_out, u
         uint32_t* ld = static_cast<uint32_t*>(lo.dev);
         __half* rd = static_cast<__half*>(ro.dev);
         unsigned grid = cdiv(rows, 8);
+        static const bool old_enc = [] { const char* e = std::getenv("VQB_TSVQ_OLD_ENCODE"); return e && *e && *e != '0'; }();
+        const bool reg_ok = !old_enc && t->metric != VQB_COSINE && dim % 128 == 0 && dim <= 16 * TE_MAX_NT &&
+                            (reinterpret_cast<uintptr_t>(rd) & 7) == 0;
+        if (reg_ok) {
+            const unsigned g4 = cdiv(rows, 4);
+            if (t->metric == VQB_SQUARED_EUCLIDEAN)
+                k_tsvq_encode_reg<VQB_SQUARED_EUCLIDEAN><<<g4, 128, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd);
+            else if (t->metric == VQB_EUCLIDEAN)
+                k_tsvq_encode_reg<VQB_EUCLIDEAN><<<g4, 128, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd);
+            else
+                k_tsvq_encode_reg<VQB_MANHATTAN><<<g4, 128, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd);
+        } else
         switch (t->metric) {
             case VQB_SQUARED_EUCLIDEAN:
                 k_tsvq_encode<VQB_SQUARED_EUCLIDEAN><<<grid, 256, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd); break;
