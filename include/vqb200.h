@@ -189,6 +189,13 @@ int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, size_t n, size
                         const float* codebooks, int sub, float* scores_out, uint64_t* rescans_out,
                         uint32_t* codes_out);
 
+/* Diagnostics: SM-clock stamps of one CTA's per-unit hand-offs during a cosine-encode pass of the tensor-core kernel
+ * (ts_out[units][8], host): 0 MMA issuer saw the accumulator free, 1 MMAs issued, 2 scan saw the accumulator full,
+ * 3 scan released it, 4 scan published its result, 5 resolve saw it, 6 resolve done, 7 splitter published x_lo.
+ * Evidence for DESIGN.md's account of what bounds the kernel; not used by any quantizer call. */
+int vqb_debug_tc_timeline(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, size_t k,
+                          const float* codebooks, uint64_t* ts_out, int units);
+
 /* ======================= TSVQ ================================================ */
 
 /* TSVQ::new (src/tsvq.rs:195-223) == TSVQNode::build (src/tsvq.rs:31-115), level-synchronous.

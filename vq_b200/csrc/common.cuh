@@ -171,7 +171,8 @@ int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t
 int vqb_tc_assign_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k,
                          const void* prep, const int* active_dev, void* codes, uint32_t code_bytes,
                          size_t code_stride_row, size_t code_stride_sub, __half* recon,
-                         float* dbg_scores = nullptr, unsigned long long* dbg_stats = nullptr, int dbg_sub = 0);
+                         float* dbg_scores = nullptr, unsigned long long* dbg_stats = nullptr, int dbg_sub = 0,
+                         unsigned long long* dbg_ts = nullptr, int dbg_ts_units = 0);
 // rows below which VQB_ASSIGN_AUTO keeps the CUDA-core kernel (the tensor kernel stages 128 KB of
 // codebooks per CTA before its first tile)
 constexpr size_t VQB_TC_MIN_ROWS = 1024;

@@ -352,6 +352,8 @@ struct TcParams {
     float* dbg_scores;            // DEBUG kernels only: [n][256] raw tensor-core scores of subspace dbg_sub
     unsigned long long* dbg_stats;  // DEBUG kernels only: [0] (row, subspace) pairs resolved by the full re-scan
     int dbg_sub;
+    unsigned long long* dbg_ts;   // DEBUG kernels only: [dbg_ts_units][8] SM-clock stamps of CTA 0's hand-offs (vqb_debug_tc_timeline)
+    int dbg_ts_units;
     uint32_t sleep_ns;            // back-off between polls of the roles that run ahead of / behind the critical path
 };
 
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                         const int acc = u & 1, cph = (u >> 1) & 1;
                         mbar_wait(ACC_EMPTY(acc), cph ^ 1);
                         tc_fence_after();
+                        if (DEBUG && p.dbg_ts && blockIdx.x == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 0] = clock64();
                         const uint64_t xhi = make_desc_sw128(sbase + OFF_RAW + st * RAW_BYTES + i * 32);
                         const uint32_t a0 = sbase + OFF_AP + ast * AP_BYTES, b0 = sbase + OFF_BP + i * BP_BYTES;
                         const uint32_t d = tmem_base + acc * TC_N;
@@ -494,6 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                         umma_commit(A_EMPTY(ast));
                         umma_commit(ACC_FULL(acc));
                         if (i == last_act) umma_commit(RAW_EMPTY(st));
+                        if (DEBUG && p.dbg_ts && blockIdx.x == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 1] = clock64();
                         ++u;
                     }
                 }
@@ -530,6 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 dst[0] = l0; dst[8] = l1;
                 fence_proxy_async();
                 mbar_arrive(A_FULL(ast));
+                if (DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 7] = clock64();
                 // this row's error margin M = KAPPA * S and indicator scale H = 2^(40 - floor(log2 S)):
                 // (th - g) * H >= 1 for every representable g < th in the score range, th * H far from overflow
                 float nx2 = 0.f;
@@ -572,6 +577,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
 
                 mbar_wait(ACC_FULL(acc), cph);
                 tc_fence_after();
+                const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 2] = clock64();
                 // ---- 256 scores -> 64 minima of four columns; the next x16 load is in flight while one is reduced
                 float gm[64];
                 uint32_t va[16], vb[16];
@@ -601,6 +608,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 }
                 tc_fence_before();
                 mbar_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 3] = clock64();
 
                 // ---- row minimum
                 float t1[22];
@@ -642,6 +650,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 mbar_wait(RES_EMPTY(rs), rph ^ 1);
                 reinterpret_cast<float2*>(sm + OFF_RES + rs * RES_BYTES)[r] = make_float2(mall, __uint_as_float(word));
                 mbar_arrive(RES_FULL(rs));
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 4] = clock64();
             }
         }
     } else {
@@ -672,6 +681,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 mbar_wait_relaxed(RES_FULL(rs), rph, p.sleep_ns);
                 const float2 rv = reinterpret_cast<const float2*>(sm + OFF_RES + rs * RES_BYTES)[r];
                 mbar_arrive(RES_EMPTY(rs));
+                const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 5] = clock64();
                 if (SKIP & 1) { mbar_arrive(RAW_EMPTY(st)); continue; }
                 const uint32_t word = __float_as_uint(rv.y);
                 const float* cb = reinterpret_cast<const float*>(sm + OFF_CB + i * CB_BYTES);
@@ -763,6 +774,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     }
                 }
                 mbar_arrive(RAW_EMPTY(st));
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 6] = clock64();
             }
             // units of this tile that belong to the other resolve warpgroup count one arrival each there
         }
@@ -823,7 +835,8 @@ int vqb_tc_prepare(vqb_ctx* ctx, int mk, const float* codebooks, size_t m, size_
 
 int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t dim, size_t m, size_t k, const void* prep,
                          const int* active_dev, void* codes, uint32_t code_bytes, size_t stride_row, size_t stride_sub,
-                         __half* recon, float* dbg_scores, unsigned long long* dbg_stats, int dbg_sub) {
+                         __half* recon, float* dbg_scores, unsigned long long* dbg_stats, int dbg_sub,
+                         unsigned long long* dbg_ts, int dbg_ts_units) {
     if (n == 0) return VQB_SUCCESS;
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled is not available");
@@ -849,10 +862,11 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
     p.parts = std::max(1, std::min(p.num_tiles, ctx->sm_count / p.n_groups));
     p.code_bytes = code_bytes;
     p.dbg_scores = dbg_scores; p.dbg_stats = dbg_stats; p.dbg_sub = dbg_sub;
+    p.dbg_ts = dbg_ts; p.dbg_ts_units = dbg_ts_units;
     static const uint32_t sleep_ns = [] { const char* e = std::getenv("VQB_TC_SLEEP_NS"); long v = e ? std::atol(e) : -1; return (uint32_t)(v >= 0 ? v : 256); }();
     p.sleep_ns = sleep_ns;
     const int grid = p.n_groups * p.parts;
-    if (dbg_scores || dbg_stats) {
+    if (dbg_scores || dbg_stats || dbg_ts) {
         if (mk == MK_COSINE) return launch_tc<MK_COSINE, true>(ctx, map, p, grid);
         if (mk == MK_TRAIN) return launch_tc<MK_TRAIN, true>(ctx, map, p, grid);
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for the training and cosine kinds only");
@@ -900,6 +914,34 @@ extern "C" int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, siz
     VQB_TRY(so.finish(ctx));
     VQB_TRY(co.finish(ctx));
     if (rescans_out) VQB_CUDA(ctx, cudaMemcpyAsync(rescans_out, stats.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VQB_SUCCESS;
+}
+
+// Diagnostics: SM-clock stamps of CTA 0's per-unit hand-offs in one cosine-encode pass (ts_out[units][8], host):
+// 0 issuer saw ACC_EMPTY, 1 issuer issued + committed, 2 scan saw ACC_FULL, 3 scan released the accumulator,
+// 4 scan published its result, 5 resolve saw it, 6 resolve done, 7 splitter published x_lo.
+extern "C" int vqb_debug_tc_timeline(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, size_t k,
+                                     const float* codebooks, uint64_t* ts_out, int units) {
+    if (!ctx || !x || !codebooks || !ts_out) return VQB_ERR_NULL_PTR;
+    if (m == 0 || dim % m) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "dim must be divisible by m");
+    const size_t d = dim / m;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    InputView xin, cin;
+    VQB_TRY(xin.bind(ctx, x, n * dim * 4));
+    VQB_TRY(cin.bind(ctx, codebooks, m * k * d * 4));
+    if (!vqb_tc_supported(MK_COSINE, static_cast<const float*>(xin.dev), n, dim, m, k, d))
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "shape not covered by the tensor-core kernel");
+    DevBuf prep, ts, codes;
+    VQB_CUDA(ctx, prep.alloc(vqb_tc_prep_bytes(m)));
+    VQB_CUDA(ctx, ts.alloc((size_t)units * 8 * 8));
+    VQB_CUDA(ctx, codes.alloc(n * m));
+    VQB_CUDA(ctx, cudaMemsetAsync(ts.p, 0, (size_t)units * 64, ctx->stream));
+    VQB_TRY(vqb_tc_prepare(ctx, MK_COSINE, static_cast<const float*>(cin.dev), m, k, prep.p));
+    VQB_TRY(vqb_tc_assign_launch(ctx, MK_COSINE, static_cast<const float*>(xin.dev), n, dim, m, k, prep.p, nullptr, codes.p, 1,
+                                 m, 1, nullptr, nullptr, nullptr, 0, ts.as<unsigned long long>(), units));
+    VQB_CUDA(ctx, cudaMemcpyAsync(ts_out, ts.p, (size_t)units * 64, cudaMemcpyDeviceToHost, ctx->stream));
     VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VQB_SUCCESS;
 }
