@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 N_ROWS, DIM, M, K = 1_000_000, 768, 96, 256
 ENC_METRIC = "cosine"           # configs[2]: L2 k-means training (src/core/vector.rs:352-363) + cosine encode
 TRAIN_ITERS_FOR_CODEBOOK = 3
+NCU_DRAM_BYTES_PER_LAUNCH = 3_075_748_000 + 98_195_200   # read + written, 1M x 768 cosine encode (profiles/r01c_*)
 METRIC_NAME = "pq_encode_throughput"
 UNIT = "Mvec/s"
 
@@ -47,7 +48,9 @@ def parse():
     p.add_argument("--metric", default=ENC_METRIC)
     p.add_argument("--assign", default="auto", choices=["auto", "exact", "tensor"])
     p.add_argument("--kmeans-iters", type=int, default=25, help="iterations of the timed k-means training call (0 = skip)")
-    p.add_argument("--cpu-sample", type=int, default=60_000, help="vectors in the cpu_baseline sample (0 = skip)")
+    p.add_argument("--cpu-sample", type=int, default=400_000,
+                   help="vectors in the cpu_baseline sample of the default run (about 10-15 s of host work; 0 = skip)")
+    p.add_argument("--ref-sample", type=int, default=60_000, help="vectors per step of --impl reference")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-paths", action="store_true", help="skip the per-path throughputs (BQ/SQ, Manhattan, L2 kinds, TSVQ)")
     return p.parse_args()
@@ -229,7 +232,7 @@ def measure_paths(eng, ext, x, pq, peaks):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    rows = min(args.rows, max(args.cpu_sample, 20_000))
+    rows = min(args.rows, max(args.ref_sample, 20_000))
     from oracle import oracle as O
     orc = O.get()
     x = make_data_host(rows, 20240)
@@ -333,9 +336,14 @@ def main():
     hbm_bytes = rows * DIM * 4 + rows * M              # X read once + u8 codes written
     tf = flops / kern_s / 1e12
     roofline = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                "note": "tf32-kind contraction scored against the measured dense bf16 peak (tf32 nominal = half); "
-                        "for sub_dim 8 the arg-min epilogue (n*m*k compare-selects), not the tensor pipe, binds",
+                "frac": tf / peaks["bf16_tflops"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH if rows == N_ROWS else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_tc_assign<cosine>, one launch, "
+                                  "profiles/r01c_tc_assign_ncu_raw.csv (ncu --set full); algorithmic bytes = "
+                                  f"{rows * DIM * 4 + rows * M}",
+                "peak_source": peaks["source"],
+                "note": "tf32-kind contraction (3 MMAs of K=8 per 128x256 tile) scored against the measured dense bf16 peak "
+                        "(tf32 nominal = half); at sub_dim 8 the MMA -> TMEM drain -> MMA cycle of an accumulator paces "
+                        "the kernel, not the tensor pipe (DESIGN.md 3.1, tools/tc_timeline.py)",
                 "hbm": {"achieved": hbm_bytes / kern_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_bytes / kern_s / 1e9 / peaks["hbm_gbs"]}}
 
@@ -419,10 +427,10 @@ def main():
             out["kmeans"] = {"value": ran / t_full, "unit": "iter/s", "ms_per_iter": per_iter * 1e3,
                              "train_call_ms": t_full * 1e3, "iters_requested": full_iters, "iters_run_min": ran,
                              "rows_total": world * rows, "iters_timed": ran, "update": "fast",
-                             "note": "value = iterations run / wall time of ONE vqb_pq_train call (25 iterations requested, "
-                                     "workspace set-up and the one-time subspace-major copy included); ms_per_iter = marginal "
-                                     "cost from the difference of two calls; all 96 subspaces advance per iteration; rows "
-                                     "sharded, one fused all-reduce per iteration"}
+                             "note": f"value = iterations run / wall time of ONE vqb_pq_train call ({full_iters} iterations requested, "
+                                     "workspace set-up and the one-time subspace-major copy included); ms_per_iter = median device "
+                                     "time of an iteration (CUDA events on the engine stream, vqb_train_opts.iter_ms); all 96 "
+                                     "subspaces advance per iteration; rows sharded, one fused all-reduce per iteration"}
         except Exception as ex:
             out["kmeans"] = {"value": None, "unit": "iter/s", "error": repr(ex)[:200]}
 
