@@ -651,7 +651,34 @@ k_tsvq_encode_reg(const float* __restrict__ x, size_t n, int dim, const float* _
     }
 }
 
+__global__ void k_iota(uint32_t* __restrict__ p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+
 struct LevelNode { uint32_t id, beg, len, depth_left; };
+
+// Per-level scratch carved out of one grow-only slab (a level used to cost ~14 cudaMalloc/cudaFree pairs = 3 ms).
+struct SlabView {
+    void* p = nullptr;
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+struct Slab {
+    DevBuf buf;
+    size_t off = 0;
+    cudaError_t ensure(size_t bytes) {  // callers synchronise the stream at the end of every level, so regrowing is safe
+        off = 0;
+        if (buf.bytes >= bytes) return cudaSuccess;
+        return buf.alloc(bytes + bytes / 2);
+    }
+    static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
+    SlabView take(size_t bytes) {
+        SlabView v;
+        v.p = static_cast<char*>(buf.p) + off;
+        off += pad(bytes);
+        return v;
+    }
+};
 
 }  // namespace
 
@@ -759,12 +786,8 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     VQB_CUDA(ctx, perm_a.alloc(n * 4));
     VQB_CUDA(ctx, perm_b.alloc(n * 4));
     VQB_CUDA(ctx, vals.alloc(n * 4));
-    {
-        std::vector<uint32_t> ident(n);
-        for (size_t i = 0; i < n; ++i) ident[i] = (uint32_t)i;
-        VQB_CUDA(ctx, cudaMemcpyAsync(perm_a.p, ident.data(), n * 4, cudaMemcpyHostToDevice, st));
-        VQB_CUDA(ctx, cudaStreamSynchronize(st));
-    }
+    k_iota<<<cdiv(n, 256), 256, 0, st>>>(perm_a.as<uint32_t>(), n);
+    VQB_LAUNCHED(ctx);
     uint32_t* perm = perm_a.as<uint32_t>();
     uint32_t* perm_next = perm_b.as<uint32_t>();
 
@@ -777,14 +800,20 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     h_median.push_back(std::nanf("")); h_count.push_back(n);
     size_t n_nodes = 1;
 
+    Slab slab;
     while (!level.empty()) {
         const size_t ln = level.size();
         // ---- means of every node of the level (tsvq.rs:36) ----
         std::vector<NodeSeg> segs(ln);
         for (size_t i = 0; i < ln; ++i) segs[i] = {level[i].beg, level[i].len};
-        DevBuf d_segs, d_mean;
-        VQB_CUDA(ctx, d_segs.alloc(ln * sizeof(NodeSeg)));
-        VQB_CUDA(ctx, d_mean.alloc(ln * dim * 4));
+        {   // everything this level can need: ln/sn-sized tables, three [nodes][dim] matrices, chunk tables
+            size_t cmax = 0;
+            for (size_t i = 0; i < ln; ++i) cmax += (level[i].len + PT_CHUNK - 1) / PT_CHUNK;
+            const size_t need = 3 * Slab::pad(ln * dim * 4) + 10 * Slab::pad(ln * 16) + Slab::pad(ln * 2 * 256 * 4) +
+                                Slab::pad(ln * sizeof(SelState)) + 2 * Slab::pad((cmax + 1) * sizeof(Chunk)) + 4096;
+            VQB_CUDA(ctx, slab.ensure(need));
+        }
+        SlabView d_segs = slab.take(ln * sizeof(NodeSeg)), d_mean = slab.take(ln * dim * 4);
         VQB_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), ln * sizeof(NodeSeg), cudaMemcpyHostToDevice, st));
         dim3 gcs(cdiv(dim, CS_SLICE), (unsigned)ln);
         if (gcs.y > 65535) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "too many nodes on one level");
@@ -823,24 +852,18 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         }
         node_chunk_beg[sn] = (uint32_t)chunks.size();
         const size_t cn = chunks.size();
-        DevBuf d_ssegs, d_smean, d_var, d_sd, d_chunks, d_ncb, d_nvalid, d_sel, d_hist, d_median, d_cleft, d_nleft;
-        VQB_CUDA(ctx, d_ssegs.alloc(sn * sizeof(NodeSeg)));
-        VQB_CUDA(ctx, d_smean.alloc(sn * dim * 4));
-        VQB_CUDA(ctx, d_var.alloc(sn * dim * 4));
-        VQB_CUDA(ctx, d_sd.alloc(sn * 4));
-        VQB_CUDA(ctx, d_chunks.alloc(cn * sizeof(Chunk)));
-        VQB_CUDA(ctx, d_ncb.alloc((sn + 1) * 4));
-        VQB_CUDA(ctx, d_nvalid.alloc(sn * 4));
-        VQB_CUDA(ctx, d_sel.alloc(sn * sizeof(SelState)));
-        VQB_CUDA(ctx, d_hist.alloc(sn * 2 * 256 * 4));
-        VQB_CUDA(ctx, d_median.alloc(sn * 4));
-        VQB_CUDA(ctx, d_cleft.alloc(cn * 4));
-        VQB_CUDA(ctx, d_nleft.alloc(sn * 4));
+        const bool all_split = sn == ln;  // then the level's means are already the splitting nodes' means, in order
+        SlabView d_ssegs = slab.take(sn * sizeof(NodeSeg));
+        SlabView d_smean = all_split ? d_mean : slab.take(sn * dim * 4);
+        SlabView d_var = slab.take(sn * dim * 4), d_sd = slab.take(sn * 4), d_chunks = slab.take(cn * sizeof(Chunk));
+        SlabView d_ncb = slab.take((sn + 1) * 4), d_nvalid = slab.take(sn * 4), d_sel = slab.take(sn * sizeof(SelState));
+        SlabView d_hist = slab.take(sn * 2 * 256 * 4), d_median = slab.take(sn * 4), d_cleft = slab.take(cn * 4);
+        SlabView d_nleft = slab.take(sn * 4);
         VQB_CUDA(ctx, cudaMemcpyAsync(d_ssegs.p, ssegs.data(), sn * sizeof(NodeSeg), cudaMemcpyHostToDevice, st));
         VQB_CUDA(ctx, cudaMemcpyAsync(d_chunks.p, chunks.data(), cn * sizeof(Chunk), cudaMemcpyHostToDevice, st));
         VQB_CUDA(ctx, cudaMemcpyAsync(d_ncb.p, node_chunk_beg.data(), (sn + 1) * 4, cudaMemcpyHostToDevice, st));
         // compact the means of the splitting nodes (device-to-device row copies)
-        for (size_t q = 0; q < sn; ++q)
+        for (size_t q = 0; q < sn && !all_split; ++q)
             VQB_CUDA(ctx, cudaMemcpyAsync(d_smean.as<float>() + q * dim, d_mean.as<float>() + (size_t)split_idx[q] * dim,
                                           dim * 4, cudaMemcpyDeviceToDevice, st));
         VQB_CUDA(ctx, cudaMemsetAsync(d_nvalid.p, 0, sn * 4, st));
