@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -311,10 +311,10 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local); clocks.start()   # sampled from warm-up to the end of the continuation below
     for _ in range(args.warmup):
         step_device()
     barrier()
-    clocks = ClockSampler(local); clocks.start()
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
@@ -323,8 +323,14 @@ def main():
     e1.record(ext)
     barrier()
     launches = eng.launch_count - l0
-    clk = clocks.stop()
     ms = e0.elapsed_time(e1)
+    # the timed region lasts tens of milliseconds, less than one nvidia-smi sampling period: keep the same step running
+    # back to back (untimed) for ~0.7 s so the clock / throttle samples are taken under exactly this load
+    for _ in range(max(1, int(700.0 / max(ms / args.steps, 0.05)))):
+        step_device()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    clk["note"] = "nvidia-smi -lms 50 from warm-up through the timed steps and a 0.7 s untimed continuation of the same step"
     if dist_on:
         t = torch.tensor([ms], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX); ms = float(t.item())
     ms_per_step = ms / args.steps
