@@ -222,6 +222,46 @@ def measure_paths(eng, ext, x, pq, peaks):
                                "frac": tf / peaks["bf16_tflops"]}
         res[name] = ent
         del q2
+    try:
+        # C5a's shape: PQ encode of 128-d vectors, m = 16, k = 256 (sub_dim 8, tensor kernel), 8M rows resident per pass
+        n5, d5, m5 = 8_000_000, 128, 16
+        x5 = torch.empty(n5, d5, device="cuda").normal_(0.0, 1.0, generator=g)
+        cb5 = x5[torch.randint(0, n5, (m5 * K,), device="cuda", generator=g)].reshape(m5, K, m5, d5 // m5)
+        cb5 = torch.stack([cb5[s_, :, s_, :] for s_ in range(m5)]).contiguous().cpu().numpy()
+        q5 = vq.ProductQuantizer.from_codebooks(cb5, vq.Distance("euclidean"), engine=eng)
+        codes5 = torch.empty(n5, m5, dtype=torch.uint8, device="cuda")
+        t = timed(lambda: eng.check(lib.vqb_pq_encode(q5._handle, x5.data_ptr(), n5, 0, codes5.data_ptr(), 1, None)), reps=3, warm=1)
+        tf = 2.0 * n5 * d5 * K / t / 1e12
+        res["pq_encode_128d_m16_euclidean"] = {"value": n5 / t / 1e6, "unit": "Mvec/s", "ms": t * 1e3,
+                                               "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"],
+                                                            "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"]}}
+        del q5, x5, codes5
+
+    except Exception as ex:  # never lose the other paths
+        res["pq_encode_128d_m16_euclidean"] = {"error": repr(ex)[:200]}
+    try:
+        # C1 (the reference's own CPU-runnable case): PQ fit (10 iterations, ordered update = the reference's summation
+        # order) + encode on 100k x 128, m = 8, k = 256, sub_dim 16 -> the exact CUDA-core assignment kernel
+        n1, d1, m1 = 100_000, 128, 8
+        x1 = (torch.randn(256, d1, device="cuda", generator=g)[torch.randint(0, 256, (n1,), device="cuda", generator=g)]
+              + 0.25 * torch.randn(n1, d1, device="cuda", generator=g)).contiguous()
+        init1, streams1 = vq.draw_init_indices(n1, m1, K, 42)
+
+        def fit_encode():
+            q1 = vq.ProductQuantizer(x1, m1, K, 10, vq.Distance("euclidean"), engine=eng, init_idx=init1,
+                                     reseed=lambda s_: streams1[s_].choose(n1))
+            q1.encode(x1)
+            torch.cuda.synchronize()
+        fit_encode()
+        t0 = time.perf_counter(); fit_encode(); t = time.perf_counter() - t0
+        res["pq_fit10_encode_100kx128_m8"] = {"value": n1 / t / 1e6, "unit": "Mvec/s", "ms": t * 1e3,
+                                              "roofline": {"bound": "fp32-issue", "achieved": None, "peak": None, "unit": "Top/s",
+                                                           "frac": None, "note": "wall time of the whole call sequence (host-side "
+                                                           "iteration control included); exact kernel, ordered update"}}
+
+    except Exception as ex:  # never lose the other paths
+        res["pq_fit10_encode_100kx128_m8"] = {"error": repr(ex)[:200]}
+
     # PQ decode (codes -> f32 reconstruction): n*m read + n*dim*4 written
     rec = torch.empty(rows, dim, device="cuda")
     t = timed(lambda: eng.check(lib.vqb_pq_decode(pq._handle, codes.data_ptr(), 1, rows, rec.data_ptr())))
