@@ -187,3 +187,36 @@ def test_tensor_training_end_to_end_matches_oracle(vq, oracle):
     want, it = oracle.pq_train(x, m, k, iters, init, reseed=lambda s: 0)
     assert np.array_equal(pq.iters_run, it)
     assert np.array_equal(pq.codebooks.view(np.uint32), want.view(np.uint32))
+
+
+def test_full_size_properties_1Mx768(vq):
+    """BASELINE.json's metric shape (1M x 768, m = 96, k = 256), checked through size-independent properties: the
+    tensor-core route and the CUDA-core exact route give identical codes for every metric they share, training is
+    deterministic (same indices -> bit-identical codebooks, tests/integration_tests.rs:40-53), the f16 reconstruction
+    is exactly the chosen centroids, and quantisation error is far below the data variance."""
+    torch = pytest.importorskip("torch")
+    n, dim, m, k = 1_000_000, 768, 96, 256
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    centers = torch.randn(1024, dim, device="cuda", generator=g)
+    x = torch.empty(n, dim, device="cuda")
+    for r0 in range(0, n, 125_000):
+        ids = torch.randint(0, 1024, (125_000,), device="cuda", generator=g)
+        x[r0:r0 + 125_000] = centers[ids] + 0.25 * torch.randn(125_000, dim, device="cuda", generator=g)
+    init, _ = vq.draw_init_indices(n, m, k, 42)
+    pq = vq.ProductQuantizer(x, m, k, 3, vq.Distance.cosine(), init_idx=init, reseed=lambda s: 0, update="fast")
+    pq2 = vq.ProductQuantizer(x, m, k, 3, vq.Distance.cosine(), init_idx=init, reseed=lambda s: 0, update="fast")
+    assert np.array_equal(pq.codebooks.view(np.uint32), pq2.codebooks.view(np.uint32))
+    assert int(pq.iters_run.min()) == 3
+    for metric in ("cosine", "squared_euclidean", "euclidean"):
+        q = vq.ProductQuantizer.from_codebooks(pq.codebooks, vq.Distance(metric))
+        c_t = q.encode(x, assign="tensor")
+        c_e = q.encode(x, assign="exact")
+        assert torch.equal(c_t, c_e), metric
+    codes, recon = pq.encode_with_recon(x)
+    cb16 = torch.from_numpy(pq.codebooks.astype(np.float16)).cuda()            # [m, k, 8]
+    want = cb16[torch.arange(m, device="cuda")[None, :], codes[:200_000].long()].reshape(200_000, dim)
+    assert torch.equal(recon[:200_000].view(torch.int16), want.view(torch.int16))
+    l2 = vq.ProductQuantizer.from_codebooks(pq.codebooks, vq.Distance.euclidean())
+    rec = l2.decode(l2.encode(x))
+    mse = float(((rec - x) ** 2).mean())
+    assert np.isfinite(mse) and mse < 0.5 * float(x.var())
