@@ -52,6 +52,7 @@ def parse():
                    help="vectors in the cpu_baseline sample of the default run (about 10-15 s of host work; 0 = skip)")
     p.add_argument("--ref-sample", type=int, default=60_000, help="vectors per step of --impl reference")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-clock-probe", action="store_true", help="skip the 0.7 s untimed continuation (profiler runs)")
     p.add_argument("--no-paths", action="store_true", help="skip the per-path throughputs (BQ/SQ, Manhattan, L2 kinds, TSVQ)")
     return p.parse_args()
 
@@ -366,7 +367,7 @@ def main():
     ms = e0.elapsed_time(e1)
     # the timed region lasts tens of milliseconds, less than one nvidia-smi sampling period: keep the same step running
     # back to back (untimed) for ~0.7 s so the clock / throttle samples are taken under exactly this load
-    for _ in range(max(1, int(700.0 / max(ms / args.steps, 0.05)))):
+    for _ in range(0 if args.no_clock_probe else max(1, int(700.0 / max(ms / args.steps, 0.05)))):
         step_device()
     torch.cuda.synchronize()
     clk = clocks.stop()
