@@ -26,6 +26,7 @@ struct vqb_tsvq {
     size_t dim = 0, n_nodes = 0;
     int metric = 0;
     DevBuf cent, left, right;
+    DevBuf cent_lane;  // [node][dim/64][16 lanes][4]: element j + 16 (4 q + e) of a centroid at (q * 16 + j) * 4 + e (built on first encode)
     std::vector<int32_t> h_left, h_right, h_split;
     std::vector<float> h_median;
     std::vector<uint64_t> h_count;
@@ -588,50 +589,77 @@ k_tsvq_encode(const float* __restrict__ x, size_t n, int dim, const float* __res
     }
 }
 
-// Register-resident form for the L2 / L1 metrics when dim is a multiple of 128 (<= 1536): lane (child, j) keeps the
-// vector's elements of AVX lane j (x[j + 16 t]) in registers for the whole descent, so a level costs one centroid
-// load, one subtract and one accumulate per element -- the per-lane order of hsdlib's kernel is unchanged.
-constexpr int TE_MAX_NT = 96;
+// Lane-major form for the L2 / L1 metrics when dim is a multiple of 128.  hsdlib's kernel gives AVX lane j the elements
+// j, j + 16, j + 32, ... and accumulates them in that order; the generic kernel above therefore issues one 4-byte load
+// per element and lane and is bound by how many of those it keeps in flight (10.6 ms per 1M x 1536, depth 8).  Here the
+// centroids are stored a second time as [dim/64][16 lanes][4] (`cent_lane`: four consecutive elements of a lane form one
+// 16-byte unit, the units of the 16 lanes are adjacent), the vector is staged once in shared memory in the same order, and
+// a lane reads both with 16-byte loads that are contiguous across the half-warp: a quarter of the load instructions, four
+// times the bytes in flight, 256 contiguous bytes per half-warp and instruction.  The per-lane summation order -- and
+// with it every bit of the distances -- is unchanged.
+__global__ void k_lane_major(const float* __restrict__ cent, size_t n_nodes, int dim, float* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_nodes * dim) return;
+    const size_t node = t / dim;
+    const int i = (int)(t - node * dim), j = i & 15, tt = i >> 4;
+    out[node * dim + (size_t)(((tt >> 2) * 16 + j) * 4 + (tt & 3))] = cent[t];
+}
+
+constexpr int TL_WARPS = 4;
 template <int METRIC>
-__global__ void __launch_bounds__(128)
-k_tsvq_encode_reg(const float* __restrict__ x, size_t n, int dim, const float* __restrict__ cent,
-                  const int* __restrict__ left, const int* __restrict__ right, uint32_t* __restrict__ leaf_out,
-                  __half* __restrict__ recon) {
-    const size_t row = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(TL_WARPS * 32)
+k_tsvq_encode_lm(const float* __restrict__ x, size_t n, int dim, const float* __restrict__ cent,
+                 const float* __restrict__ cent_lane, const int* __restrict__ left, const int* __restrict__ right,
+                 uint32_t* __restrict__ leaf_out, __half* __restrict__ recon) {
+    extern __shared__ __align__(16) float xs_all[];   // [warp][dim/64][16 lanes][4], the layout of cent_lane
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const size_t row = (size_t)blockIdx.x * TL_WARPS + warp;
     if (row >= n) return;  // warp-uniform
-    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
     const int nt = dim >> 4;
+    float* xs = xs_all + (size_t)warp * dim;
     const float* v = x + row * (size_t)dim;
-    float xr[TE_MAX_NT];
-#pragma unroll
-    for (int t0 = 0; t0 < TE_MAX_NT; t0 += 8)
-        if (t0 < nt) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) xr[t0 + u] = __ldg(v + hl + 16 * (t0 + u));
-        }
+    for (int q = lane; q < dim / 4; q += 32) {   // element i = 4q + e belongs to lane i & 15, position tt = i >> 4
+        const float4 a = __ldg(reinterpret_cast<const float4*>(v) + q);
+        const int j0 = (4 * q) & 15, tt = (4 * q) >> 4;
+        float* d = xs + ((tt >> 2) * 16 + j0) * 4 + (tt & 3);
+        d[0] = a.x; d[4] = a.y; d[8] = a.z; d[12] = a.w;
+    }
+    __syncwarp();
+    const float4* x4 = reinterpret_cast<const float4*>(xs) + hl;
     int node = 0;
     for (;;) {
         const int l = left[node], r = right[node];
         if (l >= 0 && r >= 0) {
-            const float* c = cent + (size_t)(half ? r : l) * dim + hl;
+            const int child = half ? r : l;
+            const float4* c4 = reinterpret_cast<const float4*>(cent_lane + (size_t)child * dim) + hl;
             float acc = 0.f;
+#pragma unroll 2
+            for (int t0 = 0; t0 < nt / 4; t0 += 4) {   // 16 elements of this lane per step (nt is a multiple of 8)
+                float4 cv[4], xv[4];
 #pragma unroll
-            for (int t0 = 0; t0 < TE_MAX_NT; t0 += 8)
-                if (t0 < nt) {
-                    float cv[8];
+                for (int u = 0; u < 4; ++u) if (t0 + u < nt / 4) cv[u] = __ldg(c4 + (t0 + u) * 16);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) cv[u] = __ldg(c + 16 * (t0 + u));
+                for (int u = 0; u < 4; ++u) if (t0 + u < nt / 4) xv[u] = x4[(t0 + u) * 16];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float df = __fsub_rn(xr[t0 + u], cv[u]);
-                        acc = (METRIC == VQB_MANHATTAN) ? __fadd_rn(acc, fabsf(df)) : __fmaf_rn(df, df, acc);
+                for (int u = 0; u < 4; ++u) {
+                    if (t0 + u < nt / 4) {
+                        const float d0 = __fsub_rn(xv[u].x, cv[u].x), d1 = __fsub_rn(xv[u].y, cv[u].y);
+                        const float d2 = __fsub_rn(xv[u].z, cv[u].z), d3 = __fsub_rn(xv[u].w, cv[u].w);
+                        if (METRIC == VQB_MANHATTAN) {
+                            acc = __fadd_rn(acc, fabsf(d0)); acc = __fadd_rn(acc, fabsf(d1));
+                            acc = __fadd_rn(acc, fabsf(d2)); acc = __fadd_rn(acc, fabsf(d3));
+                        } else {
+                            acc = __fmaf_rn(d0, d0, acc); acc = __fmaf_rn(d1, d1, acc);
+                            acc = __fmaf_rn(d2, d2, acc); acc = __fmaf_rn(d3, d3, acc);
+                        }
                     }
                 }
+            }
             acc = half_reduce16(acc);
             float dmine = (METRIC == VQB_EUCLIDEAN) ? __fsqrt_rn(acc) : acc;
             // hsdlib rejects a non-finite result (the Rust side then recomputes sequentially): same route as the generic kernel
             const bool bad = (hl == 0) && vqb_bad(acc);
-            if (__any_sync(0xFFFFFFFFu, bad)) dmine = pair_distance_halfwarp<METRIC>(v, cent + (size_t)(half ? r : l) * dim, dim, hl);
+            if (__any_sync(0xFFFFFFFFu, bad)) dmine = pair_distance_halfwarp<METRIC>(v, cent + (size_t)child * dim, dim, hl);
             const float dl = __shfl_sync(0xFFFFFFFFu, dmine, 0), dr = __shfl_sync(0xFFFFFFFFu, dmine, 16);
             node = (dl <= dr) ? l : r;  // tsvq.rs:122
         } else if (l >= 0) node = l;
@@ -995,16 +1023,30 @@ int vqb_tsvq_encode(vqb_tsvq* t, const float* x, size_t n, uint32_t* leaf_out, u
         __half* rd = static_cast<__half*>(ro.dev);
         unsigned grid = cdiv(rows, 8);
         static const bool old_enc = [] { const char* e = std::getenv("VQB_TSVQ_OLD_ENCODE"); return e && *e && *e != '0'; }();
-        const bool reg_ok = !old_enc && t->metric != VQB_COSINE && dim % 128 == 0 && dim <= 16 * TE_MAX_NT &&
-                            (reinterpret_cast<uintptr_t>(rd) & 7) == 0;
+        const size_t lm_smem = (size_t)TL_WARPS * dim * 4;
+        const bool reg_ok = !old_enc && t->metric != VQB_COSINE && dim % 128 == 0 && lm_smem <= 200 * 1024 &&
+                            (reinterpret_cast<uintptr_t>(rd) & 7) == 0 && (reinterpret_cast<uintptr_t>(xd) & 15) == 0;
         if (reg_ok) {
-            const unsigned g4 = cdiv(rows, 4);
+            if (!t->cent_lane.p) {  // derived copy of the immutable centroids, made once (calls are serialised by ctx->mu)
+                VQB_CUDA(ctx, t->cent_lane.alloc(t->n_nodes * dim * 4));
+                k_lane_major<<<cdiv(t->n_nodes * dim, 256), 256, 0, ctx->stream>>>(t->cent.as<float>(), t->n_nodes, (int)dim,
+                                                                                  t->cent_lane.as<float>());
+                VQB_LAUNCHED(ctx);
+            }
+            const unsigned g4 = cdiv(rows, TL_WARPS);
+            const float* cd = t->cent.as<float>();
+            const float* cl = t->cent_lane.as<float>();
+            const int* lf = t->left.as<int>();
+            const int* rt = t->right.as<int>();
+            VQB_CUDA(ctx, cudaFuncSetAttribute(k_tsvq_encode_lm<VQB_SQUARED_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_smem));
+            VQB_CUDA(ctx, cudaFuncSetAttribute(k_tsvq_encode_lm<VQB_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_smem));
+            VQB_CUDA(ctx, cudaFuncSetAttribute(k_tsvq_encode_lm<VQB_MANHATTAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_smem));
             if (t->metric == VQB_SQUARED_EUCLIDEAN)
-                k_tsvq_encode_reg<VQB_SQUARED_EUCLIDEAN><<<g4, 128, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd);
+                k_tsvq_encode_lm<VQB_SQUARED_EUCLIDEAN><<<g4, TL_WARPS * 32, lm_smem, ctx->stream>>>(xd, rows, (int)dim, cd, cl, lf, rt, ld, rd);
             else if (t->metric == VQB_EUCLIDEAN)
-                k_tsvq_encode_reg<VQB_EUCLIDEAN><<<g4, 128, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd);
+                k_tsvq_encode_lm<VQB_EUCLIDEAN><<<g4, TL_WARPS * 32, lm_smem, ctx->stream>>>(xd, rows, (int)dim, cd, cl, lf, rt, ld, rd);
             else
-                k_tsvq_encode_reg<VQB_MANHATTAN><<<g4, 128, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd);
+                k_tsvq_encode_lm<VQB_MANHATTAN><<<g4, TL_WARPS * 32, lm_smem, ctx->stream>>>(xd, rows, (int)dim, cd, cl, lf, rt, ld, rd);
         } else
         switch (t->metric) {
             case VQB_SQUARED_EUCLIDEAN:
