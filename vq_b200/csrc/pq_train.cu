@@ -189,57 +189,6 @@ k_chain_sums(const float* __restrict__ x, size_t n, size_t row_stride, size_t su
     partial[((s * k + j) * segs + seg) * d + comp] = acc;
 }
 
-// The same chains with one thread per (chain, four components): float4 member loads (two threads cover a 32-byte
-// sub-vector of sub_dim 8) and uint4 id loads -- a quarter of the load instructions of the scalar form, which is
-// LSU-bound (four 32-byte sectors per warp-wide load).  Per component the additions are the same, in the same order.
-__global__ void __launch_bounds__(256)
-k_chain_sums_v4(const float* __restrict__ x, size_t n, size_t row_stride, size_t sub_stride, int d, int k, int segs,
-                const int* __restrict__ sub_list, int n_active, const uint32_t* __restrict__ ids,
-                const uint32_t* __restrict__ seg_beg, const uint32_t* __restrict__ seg_end,
-                float* __restrict__ partial /* [m][k][segs][d] */) {
-    const int q4 = d >> 2;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)n_active * k * segs * q4;
-    if (t >= total) return;
-    int q = (int)(t % q4);
-    size_t c = t / q4;
-    int seg = (int)(c % segs); c /= segs;
-    int j = (int)(c % k);
-    size_t s = sub_list[c / k];
-    uint32_t off = seg_beg[s * k + j], cnt = seg_end[s * k + j] - off;
-    uint32_t b = off + (uint32_t)(((uint64_t)cnt * seg) / segs);
-    uint32_t e = off + (uint32_t)(((uint64_t)cnt * (seg + 1)) / segs);
-    const uint32_t* idp = ids + s * n;
-    const float* xs = x + s * sub_stride + 4 * q;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto add = [&](const float4& v) {
-        acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
-        acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-    };
-    uint32_t i = b;
-    while (i < e && ((reinterpret_cast<uintptr_t>(idp + i) & 15) != 0)) {  // up to the first 16-byte aligned id
-        add(__ldg(reinterpret_cast<const float4*>(xs + (size_t)__ldg(idp + i) * row_stride)));
-        ++i;
-    }
-    for (; i + 8 <= e; i += 8) {
-        const uint4 ia = __ldg(reinterpret_cast<const uint4*>(idp + i));
-        const uint4 ib = __ldg(reinterpret_cast<const uint4*>(idp + i + 4));
-        float4 v[8];
-        v[0] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ia.x * row_stride));
-        v[1] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ia.y * row_stride));
-        v[2] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ia.z * row_stride));
-        v[3] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ia.w * row_stride));
-        v[4] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ib.x * row_stride));
-        v[5] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ib.y * row_stride));
-        v[6] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ib.z * row_stride));
-        v[7] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)ib.w * row_stride));
-#pragma unroll
-        for (int u = 0; u < 8; ++u) add(v[u]);
-    }
-    for (; i < e; ++i) add(__ldg(reinterpret_cast<const float4*>(xs + (size_t)__ldg(idp + i) * row_stride)));
-    *reinterpret_cast<float4*>(partial + ((s * k + j) * segs + seg) * d + 4 * q) = acc;
-}
-
 // Packs [sums | count_lo | count_hi] (all f32) ; frozen subspaces are zeroed so that a cross-rank
 // sum leaves them inert.
 __global__ void k_pack(const float* __restrict__ partial, int segs, int d, int k, int m,
@@ -450,15 +399,6 @@ int train_iteration(vqb_ctx* ctx, TrainWs& ws, const TrainArgs& a, const std::ve
     // sum
     size_t chains = (size_t)na * k * ws.segs * d;
     const bool use_xt = ws.xt.p != nullptr;
-    const float* xsrc = use_xt ? ws.xt.as<float>() : a.x;
-    const size_t rstride = use_xt ? d : a.dim;
-    static const bool chain_v4 = [] { const char* e = std::getenv("VQB_CHAIN_V4"); return e && *e && *e != '0'; }();
-    if (chain_v4 && d % 4 == 0 && rstride % 4 == 0 && (reinterpret_cast<uintptr_t>(xsrc) & 15) == 0 && ((use_xt ? n * d : d) % 4 == 0)) {
-        size_t threads = (size_t)na * k * ws.segs * (d / 4);
-        k_chain_sums_v4<<<cdiv(threads, 256), 256, 0, ctx->stream>>>(xsrc, n, rstride, use_xt ? n * d : d, (int)d, (int)k, ws.segs,
-                                                                    sl, na, sorted, ws.seg_beg.as<uint32_t>(),
-                                                                    ws.seg_end.as<uint32_t>(), ws.partial.as<float>());
-    } else
     k_chain_sums<<<cdiv(chains, 256), 256, 0, ctx->stream>>>(use_xt ? ws.xt.as<float>() : a.x, n, use_xt ? d : a.dim,
                                                             use_xt ? n * d : d, (int)d, (int)k, ws.segs, sl, na,
                                                             sorted, ws.seg_beg.as<uint32_t>(),

@@ -130,9 +130,8 @@ k_colsum(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm
 // kernel's speed is rows per cycle per chain.  Here a lane's chain advances one row per LDS + dependent FADD
 // while the warp's next tiles are in flight, and hundreds of independent warps keep HBM busy on the levels that
 // have enough (node, slice) pairs; on the first levels (48, 96, ... chains of 32 columns) the chain itself binds.
-// A warp's bandwidth is (bytes it keeps in flight) / (memory latency), so the ring depth is traded against warps
-// per CTA at a fixed 64 KB: levels with few chains get one warp per CTA and a 16-deep ring (60 KB in flight per
-// chain, CTAs spread over the SMs), levels with thousands of chains get four warps with 4-deep rings.
+// Used (four warps, 4-deep rings, 64 KB per CTA) on the levels with more than ~900 chains; k_colsum_pc below serves
+// the levels with fewer.
 constexpr int CW_ROWS = 32;
 constexpr int CW_SMEM = 16 * CW_ROWS * CS_SLICE * 4;  // 64 KB = warps x stages x 4 KB
 
@@ -796,16 +795,11 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     const int vec_ok = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(xd) & 15) == 0);
     VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
     VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
-    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<0, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
-    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<0, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
     VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<0, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
-    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<1, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
-    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<1, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
     VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<1, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
     const unsigned cta_slots = (unsigned)ctx->sm_count * 3;  // 64 KB CTAs resident at once
     VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum_pc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
     VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum_pc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
-    static const bool no_pc = [] { const char* e = std::getenv("VQB_TSVQ_NO_PC"); return e && *e && *e != '0'; }();
     static const bool old_colsum = [] { const char* e = std::getenv("VQB_TSVQ_OLD_COLSUM"); return e && *e && *e != '0'; }();
     const bool warp_chains = vec_ok && dim % CS_SLICE == 0 && !old_colsum;  // else: block-wide ring kernel (any dim / alignment)
     const int n_slices = (int)(dim / CS_SLICE);
@@ -847,12 +841,8 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         if (gcs.y > 65535) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "too many nodes on one level");
         if (warp_chains) {
             const unsigned tw = (unsigned)(ln * n_slices);
-            if (tw <= 2 * cta_slots && !no_pc)
+            if (tw <= 2 * cta_slots)
                 k_colsum_pc<0><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
-            else if (tw <= cta_slots)
-                k_colsum_w<0, 1, 16><<<tw, 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
-            else if (tw <= 2 * cta_slots)
-                k_colsum_w<0, 2, 8><<<cdiv(tw, 2), 64, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
             else
                 k_colsum_w<0, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
         } else
@@ -900,12 +890,8 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         dim3 gvs(cdiv(dim, CS_SLICE), (unsigned)sn);
         if (warp_chains) {
             const unsigned tw = (unsigned)(sn * n_slices);
-            if (tw <= 2 * cta_slots && !no_pc)
+            if (tw <= 2 * cta_slots)
                 k_colsum_pc<1><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
-            else if (tw <= cta_slots)
-                k_colsum_w<1, 1, 16><<<tw, 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
-            else if (tw <= 2 * cta_slots)
-                k_colsum_w<1, 2, 8><<<cdiv(tw, 2), 64, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
             else
                 k_colsum_w<1, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
         } else
