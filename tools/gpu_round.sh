@@ -19,4 +19,5 @@ python tools/launch_summary.py gpurun_out/probe_launches.csv 14
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tc_assign -s 4 -c 2 -f -o gpurun_out/tc_assign \
   python bench.py --steps 2 --warmup 1 --kmeans-iters 0 --cpu-sample 0 --no-e2e --no-paths --no-clock-probe > gpurun_out/bench_ncu2.log 2>&1
 timeout 300 python tools/tc_timeline.py > gpurun_out/tc_timeline.txt 2>&1; tail -3 gpurun_out/tc_timeline.txt
+timeout 600 ncu --set full --clock-control none -k regex:"k_f32_to_u8|k_u8_to_f32|k_assign_exact|k_pq_decode|k_colsum|k_tsvq_encode|k_radix_scatter|k_chain_sums" -c 45 -f -o gpurun_out/others python tools/probe_paths.py > gpurun_out/probe_full.log 2>&1; tail -2 gpurun_out/probe_full.log
 ls -la gpurun_out

@@ -10,6 +10,25 @@ eng = vq.Engine(0)
 lib = eng.lib
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 g = torch.Generator(device="cuda"); g.manual_seed(5)
+if what in ("all", "codec"):
+    n, d = 1_000_000, 1536
+    e = torch.empty(n, d, device="cuda").normal_(0.0, 0.5, generator=g)
+    q = torch.empty(n, d, dtype=torch.uint8, device="cuda")
+    ne = n * d
+    eng.check(lib.vqb_bq_quantize(eng.h, e.data_ptr(), ne, 0.0, 0, 1, q.data_ptr()))
+    eng.check(lib.vqb_sq_quantize(eng.h, e.data_ptr(), ne, -1.0, 1.0, float(np.float32(2.0) / np.float32(255.0)), 256, q.data_ptr()))
+    eng.check(lib.vqb_sq_dequantize(eng.h, q.data_ptr(), ne, -1.0, float(np.float32(2.0) / np.float32(255.0)), e.data_ptr()))
+    torch.cuda.synchronize()
+    del e, q
+if what in ("all", "manhattan"):
+    rows, DIM, M, K = 1_000_000, 768, 96, 256
+    x = torch.randn(rows, DIM, device="cuda", generator=g)
+    cb = x[:K * 4:4].reshape(K, M, 8).permute(1, 0, 2).contiguous().cpu().numpy()
+    pq = vq.ProductQuantizer.from_codebooks(cb, vq.Distance("manhattan"), engine=eng)
+    codes = pq.encode(x)
+    rec = pq.decode(codes)
+    torch.cuda.synchronize()
+    del x, codes, rec, pq
 if what in ("all", "tsvq"):
     n, d = 1_000_000, 1536
     x = torch.empty(n, d, device="cuda").normal_(0.0, 0.5, generator=g)
