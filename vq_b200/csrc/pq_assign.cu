@@ -91,27 +91,26 @@ k_assign_exact(const float* __restrict__ x, size_t n, int dim, int k, int sub_di
             __syncthreads();
         }
         if (live) {
-            for (int j = 0; j < kc; ++j) {
+            auto eval = [&](int j) -> float {
                 PtrAcc cp{cs + (size_t)j * d};
-                float dist;
-                if (MK == MK_TRAIN) {
-                    dist = (D > 0) ? dist2_seq<D>(xr, cp, d) : dist2_seq<0>(xp, cp, d);
-                } else if (MK == MK_COSINE) {
-                    if (d == 0) dist = 0.f;
-                    else {
-                        float dot = (D > 0) ? hsd_cosine_dot<D>(xr, cp, d) : hsd_cosine_dot<0>(xp, cp, d);
-                        bool ok = a_tail_ok && aux[j].tail_ok != 0.f;
-                        float sim = 0.f;
-                        if (ok) sim = hsd_cosine_from_sums(dot, na, aux[j].nb, sa, aux[j].sb, ok);
-                        dist = ok ? __fsub_rn(1.0f, sim)
-                                  : ((D > 0) ? rust_cos<D>(xr, cp, d) : rust_cos<0>(xp, cp, d));
-                    }
-                } else {
-                    dist = (D > 0) ? vq_distance<D>(MK, xr, cp, d) : vq_distance<0>(MK, xp, cp, d);
+                if (MK == MK_TRAIN) return (D > 0) ? dist2_seq<D>(xr, cp, d) : dist2_seq<0>(xp, cp, d);
+                if (MK == MK_COSINE) {
+                    if (d == 0) return 0.f;
+                    float dot = (D > 0) ? hsd_cosine_dot<D>(xr, cp, d) : hsd_cosine_dot<0>(xp, cp, d);
+                    bool ok = a_tail_ok && aux[j].tail_ok != 0.f;
+                    float sim = 0.f;
+                    if (ok) sim = hsd_cosine_from_sums(dot, na, aux[j].nb, sa, aux[j].sb, ok);
+                    return ok ? __fsub_rn(1.0f, sim) : ((D > 0) ? rust_cos<D>(xr, cp, d) : rust_cos<0>(xp, cp, d));
                 }
-                // pq.rs:183-191 / vector.rs:354-361: index 0 seeds the minimum, then strict '<'
-                if ((k0 + j) == 0) { best_dist = dist; best = 0; }
-                else if (dist < best_dist) { best_dist = dist; best = (uint32_t)(k0 + j); }
+                return (D > 0) ? vq_distance<D>(MK, xr, cp, d) : vq_distance<0>(MK, xp, cp, d);
+            };
+            // pq.rs:183-191 / vector.rs:354-361: index 0 seeds the minimum (whatever its value), then strict '<'
+            int j = 0;
+            if (k0 == 0) { best_dist = eval(0); best = 0; j = 1; }
+#pragma unroll 4
+            for (; j < kc; ++j) {
+                const float dist = eval(j);
+                if (dist < best_dist) { best_dist = dist; best = (uint32_t)(k0 + j); }
             }
         }
     }
