@@ -218,3 +218,21 @@ def test_gloo_two_rank_exchange_protocol(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o[-3000:]
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` needs no GPU: it times the restated reference loop on the host cores and prints one
+    JSON line with the same metric / unit / config keys as the CUDA arm plus impl, cpu_baseline and a zero-copy e2e."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--ref-sample", "20000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "pq_encode_throughput" and line["unit"] == "Mvec/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Mvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["m"] == 96 and line["config"]["k"] == 256 and line["config"]["dim"] == 768
