@@ -18,7 +18,10 @@
  * DEVICE pointer of the context's GPU; the library classifies it with
  * cudaPointerGetAttributes.  Calls whose data pointers are all device pointers are
  * enqueued on the context stream and return without synchronising (use
- * vqb_ctx_synchronize); calls that touch host memory are complete on return.
+ * vqb_ctx_synchronize); calls that touch host memory are complete on return.  Host-pointer
+ * batch calls are pipelined in row chunks over three streams through grow-only device staging
+ * buffers owned by the context (no allocation per call after the first); calls on one context
+ * are serialised by its mutex, so several threads may share a context.
  *
  * There is NO CPU fallback: every function fails with VQB_ERR_UNSUPPORTED_DEVICE
  * when no sm_100 GPU is present.
