@@ -204,6 +204,23 @@ for it in range(5):
     for s in range(m):
         rel = np.linalg.norm(cb_state[s] - ref_state[s]) / np.linalg.norm(ref_state[s])
         assert rel <= 1e-4, rel
+
+# 3. shard by SUBSPACE (SURVEY 8e cross-check): every rank trains its subspaces on all rows with the reference's own
+#    summation order; gathered blocks must equal the single-process result bit for bit, iteration counts included.
+from vq_b200.dist import subspace_bounds, gather_codebooks
+m3, k3, it3 = 5, 16, 4                            # 5 subspaces over 2 ranks: uneven split (3 + 2)
+x3 = np.ascontiguousarray(x[:, :15])              # dim 15, sub_dim 3
+init3 = np.stack([np.random.default_rng(100 + s).choice(n, k3, replace=False) for s in range(m3)]).astype(np.uint64)
+want_cb, want_it = orc.pq_train(x3, m3, k3, it3, init3, reseed=lambda s: 0)
+s0, s1 = subspace_bounds(m3, rank, world)
+assert (s0, s1) == ((0, 3) if rank == 0 else (3, 5))
+d3 = 3
+blk, blk_it = orc.pq_train(np.ascontiguousarray(x3[:, s0 * d3:s1 * d3]), s1 - s0, k3, it3, init3[s0:s1], reseed=lambda s: 0)
+full = gather_codebooks(blk, m3)
+assert np.array_equal(full.view(np.uint32), want_cb.view(np.uint32))
+its = [None] * world
+td.all_gather_object(its, np.asarray(blk_it, dtype=np.uint32))
+assert np.array_equal(np.concatenate(its), want_it)
 td.destroy_process_group()
 print("RANK_OK", rank)
 '''

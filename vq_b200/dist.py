@@ -113,3 +113,58 @@ def unpack_reduced(buf: np.ndarray, n_sums: int) -> tuple[np.ndarray, np.ndarray
     lo = buf[n_sums:n_sums + n_c].astype(np.uint64)
     hi = buf[n_sums + n_c:].astype(np.uint64)
     return buf[:n_sums], hi * 65536 + lo
+
+
+# ---- shard by SUBSPACE: the collective-free cross-check of SURVEY.md 8(e) ---------------------------------------
+# Subspaces are fully independent (src/pq.rs:121-132: one lbg_quantize per subspace with seed + i), so rank r can train
+# subspaces [s0, s1) on ALL rows of its column slice with the ordered update and the result is bit-identical to a
+# single-GPU run -- no all-reduce, the reference's exact summation order.  It needs every rank to hold all rows, which is
+# why row sharding (above) is the production path and this one the cross-check.
+def subspace_bounds(m: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced subspace range [s0, s1) of `rank`."""
+    return shard_bounds(m, rank, world)
+
+
+def gather_codebooks(local: np.ndarray, m: int, group=None) -> np.ndarray:
+    """All ranks contribute their [m_local, k, sub_dim] block (rank order = subspace order); returns [m, k, sub_dim].
+    Blocks travel as objects, not through a sum, so signed zeros and NaNs arrive untouched."""
+    world = td.get_world_size(group)
+    parts = [None] * world
+    td.all_gather_object(parts, np.ascontiguousarray(local, dtype=np.float32), group=group)
+    parts = [p for p in parts if p is not None and p.shape[0] > 0]
+    full = np.concatenate(parts, axis=0) if parts else np.empty((0,) + tuple(local.shape[1:]), np.float32)
+    if full.shape[0] != m:
+        raise RuntimeError(f"gathered {full.shape[0]} subspaces, expected {m}")
+    return full
+
+
+def train_pq_by_subspace(training_data, num_subspaces: int, num_centroids: int, max_iters: int = 10, distance=None,
+                         seed: int = 42, *, engine=None, group=None, assign: str = "auto"):
+    """ProductQuantizer trained with the subspaces split over the ranks of `group` (every rank passes the SAME full
+    training set).  Index streams are drawn exactly as a single process draws them (seed + global subspace id), so
+    the returned quantizer equals `ProductQuantizer(training_data, m, k, max_iters, distance, seed)` bit for bit."""
+    from . import api
+    rank, world = td.get_rank(group), td.get_world_size(group)
+    n, dim = tuple(training_data.shape)
+    m, k = int(num_subspaces), int(num_centroids)
+    if m == 0 or dim % m:
+        raise api.InvalidParameter("m", f"dimension ({dim}) must be divisible by m")
+    d = dim // m
+    s0, s1 = subspace_bounds(m, rank, world)
+    init, streams = api.draw_init_indices(n, m, k, int(seed))
+    if s1 > s0:
+        cols = training_data[:, s0 * d:s1 * d]
+        cols = cols.contiguous() if hasattr(cols, "contiguous") else np.ascontiguousarray(cols)
+        local = api.ProductQuantizer(cols, s1 - s0, k, max_iters, distance, seed, engine=engine, update="ordered",
+                                     assign=assign, init_idx=init[s0:s1],
+                                     reseed=lambda s: streams[s0 + s].choose(n))
+        block, iters = local.codebooks, local.iters_run
+    else:  # more ranks than subspaces
+        block, iters = np.empty((0, k, d), np.float32), np.empty(0, np.uint32)
+    full = gather_codebooks(block, m, group)
+    its = [None] * world
+    td.all_gather_object(its, np.asarray(iters, dtype=np.uint32), group=group)
+    pq = api.ProductQuantizer.from_codebooks(full, distance, engine=engine)
+    pq.iters_run = np.concatenate([np.asarray(i, dtype=np.uint32) for i in its])
+    pq.init_idx = init
+    return pq
