@@ -138,6 +138,32 @@ def cpu_encode_rate(rows, metric, threads=None):
     return rows / dt / 1e6, threads, kind, dt, f"hsdlib: {backend}"
 
 
+def cpu_as_shipped(metric, enc_rows=8_000, km_rows=50_000):
+    """SURVEY 8(d) figure (i): the reference's own parallelism.  Encode is a single-threaded loop over the vectors
+    (src/bin/eval_pq.rs:53-58); training parallelises the assignment over points only (src/core/vector.rs:417-423),
+    everything else serial -- restated by the oracle's lbg loop.  Bounded samples, linear in n."""
+    from oracle import oracle as O
+    orc = O.get()
+    x = make_data_host(max(enc_rows, km_rows), 20240)
+    rng = np.random.default_rng(42)
+    d = DIM // M
+    cb = np.stack([x[rng.choice(x.shape[0], K, replace=False), s * d:(s + 1) * d] for s in range(M)]).astype(np.float32)
+    sem = orc.default_sem()
+    t0 = time.perf_counter()
+    orc.pq_encode(cb, metric, x[:enc_rows], sem=sem, want_recon=True, threads=1)
+    t_enc = time.perf_counter() - t0
+    threads = os.cpu_count() or 1
+    init = np.stack([rng.choice(km_rows, K, replace=False) for _ in range(M)]).astype(np.uint64)
+    t0 = time.perf_counter()
+    orc.pq_train(np.ascontiguousarray(x[:km_rows]), M, K, 1, init, reseed=lambda s: 0, threads=threads)
+    t_km = time.perf_counter() - t0
+    return {"encode_single_thread": {"value": enc_rows / t_enc / 1e6, "unit": UNIT, "cores": 1,
+                                     "sample": f"{enc_rows} vectors ({t_enc:.1f} s), one thread as in src/bin/eval_pq.rs:53-58"},
+            "kmeans": {"value": 1.0 / (t_km * N_ROWS / km_rows), "unit": "iter/s", "cores": threads,
+                       "sample": f"one iteration of all {M} subspaces on {km_rows} of {N_ROWS} rows ({t_km:.1f} s), scaled "
+                                 "linearly to 1M rows; assignment parallel over points, the rest serial (src/core/vector.rs:417-457)"}}
+
+
 def measure_paths(eng, ext, x, pq, peaks):
     """Device-resident throughput of the remaining hot-path rows on one GPU: CUDA events on the
     engine stream, 2 warm-up + 5 timed passes each, inputs larger than L2.  Algorithmic bytes/ops per SURVEY 8(d)."""
@@ -495,6 +521,10 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                    "sample": f"{args.cpu_sample} of {rows} vectors ({dt:.1f} s); restated src/pq.rs:167-199 "
                                              f"loop parallel over vectors; {backend}"}
+            try:
+                out["cpu_baseline"]["as_shipped"] = cpu_as_shipped(args.metric)
+            except Exception as ex:
+                out["cpu_baseline"]["as_shipped"] = {"error": repr(ex)[:200]}
         except Exception as ex:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": repr(ex)[:200]}
 
