@@ -199,6 +199,10 @@ int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, size_t n, size
 int vqb_debug_tc_timeline(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, size_t k,
                           const float* codebooks, uint64_t* ts_out, int units);
 
+/* Diagnostics: selects a timing variant of the tensor-core kernel (warp-role order; every variant produces the same
+ * codes).  Process-wide; not used by any quantizer call. */
+int vqb_debug_tc_variant(int variant);
+
 /* ======================= TSVQ ================================================ */
 
 /* TSVQ::new (src/tsvq.rs:195-223) == TSVQNode::build (src/tsvq.rs:31-115), level-synchronous.

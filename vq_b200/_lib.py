@@ -66,6 +66,7 @@ SIGNATURES = {
     "vqb_pq_decode": (C.c_int, [_P, _P, C.c_uint32, _SZ, _P]),
     "vqb_debug_tc_scores": (C.c_int, [_P, C.c_int, _P, _SZ, _SZ, _SZ, _SZ, _P, C.c_int, _P, _P, _P]),
     "vqb_debug_tc_timeline": (C.c_int, [_P, _P, _SZ, _SZ, _SZ, _SZ, _P, _P, C.c_int]),
+    "vqb_debug_tc_variant": (C.c_int, [C.c_int]),
     "vqb_tsvq_train": (C.c_int, [_P, _P, _SZ, _SZ, _SZ, C.c_int, C.POINTER(_P)]),
     "vqb_tsvq_create": (C.c_int, [_P, _P, _P, _P, _SZ, _SZ, C.c_int, C.POINTER(_P)]),
     "vqb_tsvq_destroy": (C.c_int, [_P]),

@@ -33,7 +33,39 @@ struct vqb_ctx {
     void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t stage_ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // grow-only device workspace of the training / tree-building calls (one slab, bump-allocated per call)
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // multi-GPU: NCCL communicator owned by the context (comm.cu; libnccl is loaded at run time), or null
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 };
+
+// Bump allocator over the context's grow-only workspace slab.  Usage: size pass (base == nullptr) to learn the
+// total, vqb_ws_reserve, then the same sequence of take() calls with the real base.  Callers hold ctx->mu and all
+// previous users of the slab are complete (every call that uses it synchronises before returning).
+struct WsBump {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T> T* take(size_t count) {
+        const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+inline cudaError_t vqb_ws_reserve(vqb_ctx* ctx, size_t bytes) {
+    if (ctx->ws_bytes >= bytes) return cudaSuccess;
+    if (ctx->ws) cudaFree(ctx->ws);
+    ctx->ws = nullptr; ctx->ws_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->ws, bytes);
+    if (e == cudaSuccess) ctx->ws_bytes = bytes;
+    return e;
+}
+
+// multi-GPU plumbing (comm.cu): in-place float sum over the ranks of the context's communicator on ctx->stream
+int vqb_comm_allreduce_f32(vqb_ctx* ctx, float* buf, size_t count);
+void vqb_comm_release(vqb_ctx* ctx);
 
 // Returns ctx->stage[i] grown to at least `bytes` (callers hold ctx->mu; previous users of the slot are
 // complete because every host-pointer call synchronises its streams before returning).

@@ -42,6 +42,8 @@ int vqb_ctx_destroy(vqb_ctx* ctx) {
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    vqb_comm_release(ctx);
+    if (ctx->ws) cudaFree(ctx->ws);
     for (int i = 0; i < 6; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     for (int i = 0; i < 7; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     delete ctx;

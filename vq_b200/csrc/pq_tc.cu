@@ -30,21 +30,20 @@
 //
 // Warp roles (768 threads = 6 warpgroups, registers re-balanced with setmaxnreg):
 //   WG0  w0 TMA producer | w1 MMA issuer + TMEM owner | w2-3 idle
-//   WG1  splitter: x_lo operand tile + the row's error margin
-//   WG2-3 scan: one warpgroup per TMEM accumulator; thread = row = TMEM lane; pure register work
-//   WG4-5 resolve: fp32 re-score of the candidate group (or the full reference re-scan), code /
-//         f16 reconstruction stores
+//   WG1  splitter, once per row tile: the x_lo operand tile of all four subspaces (same SWIZZLE_128B layout as
+//        the raw tile, so the tensor core reads it through the same descriptor form) + the rows' error margins
+//   two scan warpgroups: one per TMEM accumulator; thread = row = TMEM lane; pure register work
+//   two resolve warpgroups: fp32 re-score of the candidate group (or the full reference re-scan), code /
+//        f16 reconstruction stores
 // The per-unit chain split -> MMA -> scan -> resolve is a software pipeline over shared-memory rings;
-// all hand-offs are mbarriers; tcgen05.commit releases smem / signals TMEM.  Waiting roles back off
-// with nanosleep so their polling does not take issue slots from the scan warps (r01b profile: 20 %
-// of all issued instructions were try_wait spins).
+// all hand-offs are mbarriers; tcgen05.commit releases smem / signals TMEM.  Every wait is a
+// mbarrier.try_wait with a suspend-time hint: waiting warps sleep in hardware and take no issue slots.
 #include "common.cuh"
 #include "distance.cuh"
 
 #include <cuda.h>
 
 #include <algorithm>
-#include <cstdlib>
 #include <cstdlib>
 
 namespace {
@@ -53,42 +52,45 @@ constexpr int TC_D = 8;            // sub_dim handled here
 constexpr int TC_G = 4;            // subspaces per CTA (4 * 8 floats = 128 B)
 constexpr int TC_N = 256;          // MMA N = centroid slots per subspace
 constexpr int TC_ROWS = 128;       // MMA M = rows per tile = TMEM lanes
-constexpr int RAW_STAGES = 3;
-constexpr int A_STAGES = 4;        // splitter -> MMA: x_lo operand tiles
-constexpr int MG_STAGES = 4;       // splitter -> scan: per-row margin
-constexpr int RES_STAGES = 4;      // scan -> resolve: per-row candidate group
-constexpr int TC_THREADS = 768;
-// setmaxnreg budget: the pool is what the CTA was launched with (768 threads x 80 registers = 61440), so
-// 128*24 + 128*48 + 256*128 + 256*72 = 60416 must not exceed it or the last setmaxnreg.inc never returns
-constexpr int REGS_LAUNCH = 80, REGS_CTRL = 24, REGS_SPLIT = 48, REGS_SCAN = 128, REGS_RESOLVE = 72;
-static_assert(128 * REGS_CTRL + 128 * REGS_SPLIT + 256 * REGS_SCAN + 256 * REGS_RESOLVE <= TC_THREADS * REGS_LAUNCH,
+constexpr int RAW_STAGES = 3;      // TMA -> everyone: raw fp32 row tiles (128 rows x 128 B, SWIZZLE_128B)
+constexpr int AT_STAGES = 2;       // splitter -> MMA: x_lo tiles, same shape and swizzle as the raw tile
+constexpr int MG_STAGES = 2;       // splitter -> scan: margins of one row tile, [TC_G][128 rows]
+constexpr int RES_STAGES = 4;      // scan -> resolve: per-row candidate group of one unit
+constexpr int TC_THREADS = 640;    // 5 warpgroups: control | splitter | resolve | scan (columns 0-127) | scan (columns 128-255)
+// setmaxnreg budget: the pool is what the CTA was launched with (640 threads x 96 registers = 61440), so
+// 128*24 + 128*56 + 128*80 + 256*160 = 61440 must not exceed it or the last setmaxnreg.inc never returns
+constexpr int REGS_LAUNCH = 96, REGS_CTRL = 24, REGS_SPLIT = 56, REGS_SCAN = 160, REGS_RESOLVE = 80;
+static_assert(128 * REGS_CTRL + 128 * REGS_SPLIT + 256 * REGS_SCAN + 128 * REGS_RESOLVE <= TC_THREADS * REGS_LAUNCH,
               "setmaxnreg budget exceeds the registers the CTA owns");
 
 constexpr uint32_t RAW_BYTES = TC_ROWS * 128;           // 16 KB per stage
-constexpr uint32_t BP_BYTES = 32 * 6 * 128;             // 24 KB: [32 row groups][6 k-chunks][8 rows][16 B]
+constexpr uint32_t BP_CHUNKS = 5;                       // hi0 hi1 lo0 lo1 norm; the norm MMA's second K chunk is the
+                                                        // next row group's hi0 (finite) times the ones tile's zeros
+constexpr uint32_t BP_SBO = BP_CHUNKS * 128;            // 640 B between 8-row groups
+constexpr uint32_t BP_BYTES = 32 * BP_SBO;              // 20 KB: [32 row groups][5 k-chunks][8 rows][16 B]
+constexpr uint32_t BP_PAD = 128;                        // zeros behind the last image (read by the last norm chunk pair)
 constexpr uint32_t CB_BYTES = TC_N * TC_D * 4;          // 8 KB raw f32 codebook, row-major
 constexpr uint32_t AUX_BYTES = TC_N * 8;                // 2 KB (nb, sb) per centroid (cosine, exact path)
-constexpr uint32_t RINV_BYTES = TC_N * 4;               // 1 KB -1/||c|| per centroid (cosine, fp32 re-score)
-constexpr uint32_t AP_BYTES = 16 * 2 * 128;             // 4 KB: [16 row groups][2 k-chunks][8 rows][16 B]
-constexpr uint32_t ONES_BYTES = 16 * 2 * 128;           // 4 KB
-constexpr uint32_t MG_BYTES = TC_ROWS * 8;              // float2 {H, M} per row
-constexpr uint32_t RES_BYTES = TC_ROWS * 8;             // float2 {row minimum, M | group index} per row
+constexpr uint32_t RINV_BYTES = TC_N * 4;               // 1 KB per centroid: -1/||c|| (cosine) or ||c||^2 (L2 kinds), fp32 re-score
+constexpr uint32_t ONES_BYTES = 16 * 2 * 128;           // 4 KB: [16 row groups][2 k-chunks][8 rows][16 B]
+constexpr uint32_t MG_BYTES = TC_G * TC_ROWS * 8;       // float2 {H, M} per (subspace, row)
+constexpr uint32_t RES_BYTES = TC_ROWS * 16;            // per row: {half minimum, M | group index} of the two column halves
 constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES + RINV_BYTES;  // per-subspace prepared image in HBM
 
 constexpr uint32_t OFF_RAW = 0;
-constexpr uint32_t OFF_BP = OFF_RAW + RAW_STAGES * RAW_BYTES;
-constexpr uint32_t OFF_CB = OFF_BP + TC_G * BP_BYTES;
+constexpr uint32_t OFF_AT = OFF_RAW + RAW_STAGES * RAW_BYTES;
+constexpr uint32_t OFF_BP = OFF_AT + AT_STAGES * RAW_BYTES;
+constexpr uint32_t OFF_CB = OFF_BP + TC_G * BP_BYTES + BP_PAD;
 constexpr uint32_t OFF_AUX = OFF_CB + TC_G * CB_BYTES;
 constexpr uint32_t OFF_RINV = OFF_AUX + TC_G * AUX_BYTES;
-constexpr uint32_t OFF_AP = OFF_RINV + TC_G * RINV_BYTES;
-constexpr uint32_t OFF_ONES = OFF_AP + A_STAGES * AP_BYTES;
+constexpr uint32_t OFF_ONES = OFF_RINV + TC_G * RINV_BYTES;
 constexpr uint32_t OFF_MG = OFF_ONES + ONES_BYTES;
 constexpr uint32_t OFF_RES = OFF_MG + MG_STAGES * MG_BYTES;
 constexpr uint32_t OFF_SINFO = OFF_RES + RES_STAGES * RES_BYTES;  // TC_G x {sqrt(cmax2), unsafe}
 constexpr uint32_t OFF_BAR = OFF_SINFO + 64;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // barriers + slack for the 1024-byte alignment
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
-static_assert(OFF_CB % 128 == 0 && OFF_AP % 128 == 0, "operand tiles must be 128-byte aligned");
+static_assert(OFF_AT % 1024 == 0 && OFF_BP % 128 == 0 && OFF_CB % 128 == 0 && OFF_ONES % 128 == 0, "operand tiles must be aligned");
 constexpr uint32_t RES_AMBIGUOUS = 0x80000000u;         // sign bit of the margin word
 
 template <int D>
@@ -114,32 +116,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity), "r"(0x4000u)  // suspend-time hint (ns): waiters sleep in hardware, not in the issue slots
-            : "memory");
-    }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
-// waiting roles that are not on the critical path: poll, then sleep between polls
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
-    uint32_t ok = 0;
-    for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        __nanosleep(sleep_ns);
-    }
+// One probe, then sleep between probes.  try_wait returns after a few cycles on this part whatever suspend-time hint it is
+// given (r02a profile: 23 % of all issued instructions were try_wait probes of waiting warps), so waiting warps back off
+// with nanosleep; SLEEP_NS is chosen per hand-off from the slack the waiting role has.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    do { __nanosleep(SLEEP_NS); } while (!mbar_try(bar, parity));
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -185,30 +179,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* v) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
         : "r"(taddr)
         : "memory");
 }
 // tcgen05.wait::ld tied to the destination registers, so no use of them can be scheduled above it
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_ld_wait128(uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]), "+r"(v[32]), "+r"(v[33]), "+r"(v[34]), "+r"(v[35]), "+r"(v[36]), "+r"(v[37]), "+r"(v[38]), "+r"(v[39]), "+r"(v[40]), "+r"(v[41]), "+r"(v[42]), "+r"(v[43]), "+r"(v[44]), "+r"(v[45]), "+r"(v[46]), "+r"(v[47]), "+r"(v[48]), "+r"(v[49]), "+r"(v[50]), "+r"(v[51]), "+r"(v[52]), "+r"(v[53]), "+r"(v[54]), "+r"(v[55]), "+r"(v[56]), "+r"(v[57]), "+r"(v[58]), "+r"(v[59]), "+r"(v[60]), "+r"(v[61]), "+r"(v[62]), "+r"(v[63]), "+r"(v[64]), "+r"(v[65]), "+r"(v[66]), "+r"(v[67]), "+r"(v[68]), "+r"(v[69]), "+r"(v[70]), "+r"(v[71]), "+r"(v[72]), "+r"(v[73]), "+r"(v[74]), "+r"(v[75]), "+r"(v[76]), "+r"(v[77]), "+r"(v[78]), "+r"(v[79]), "+r"(v[80]), "+r"(v[81]), "+r"(v[82]), "+r"(v[83]), "+r"(v[84]), "+r"(v[85]), "+r"(v[86]), "+r"(v[87]), "+r"(v[88]), "+r"(v[89]), "+r"(v[90]), "+r"(v[91]), "+r"(v[92]), "+r"(v[93]), "+r"(v[94]), "+r"(v[95]), "+r"(v[96]), "+r"(v[97]), "+r"(v[98]), "+r"(v[99]), "+r"(v[100]), "+r"(v[101]), "+r"(v[102]), "+r"(v[103]), "+r"(v[104]), "+r"(v[105]), "+r"(v[106]), "+r"(v[107]), "+r"(v[108]), "+r"(v[109]), "+r"(v[110]), "+r"(v[111]), "+r"(v[112]), "+r"(v[113]), "+r"(v[114]), "+r"(v[115]), "+r"(v[116]), "+r"(v[117]), "+r"(v[118]), "+r"(v[119]), "+r"(v[120]), "+r"(v[121]), "+r"(v[122]), "+r"(v[123]), "+r"(v[124]), "+r"(v[125]), "+r"(v[126]), "+r"(v[127])
                  :
                  : "memory");
 }
@@ -216,6 +197,11 @@ __device__ __forceinline__ float to_tf32(float x) {  // round-to-nearest tf32, l
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -228,6 +214,9 @@ __device__ __forceinline__ float fsat_ind(float g, float negH, float thH) {  // 
     float r;
     asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(g), "f"(negH), "f"(thH));
     return r;
+}
+__device__ __forceinline__ float tf32_lo(float v) {  // v - trunc_tf32(v): exact, what the tensor core drops when it reads v as tf32
+    return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
 }
 
 // ------------------------------------------------------------------------------- prepare kernel
@@ -256,17 +245,18 @@ __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ c
     if (!finite) atomicOr(&bad, 1u);
     float b[TC_D];
     float npiece[3] = {0.f, 0.f, 0.f};
-    float nrinv = 0.0f;
+    float rescore = 0.0f;   // cosine: -1/||c|| (score = x.c * rescore) ; L2 kinds: ||c||^2 (score = rescore - 2 x.c)
     if (MK == MK_COSINE) {
         // scores = -x.c/||c||;  ||c||^2 < FLT_MIN counts as a zero vector (cosine.c:38-45): score 0
         double inv = (finite && n2 >= (double)FLT_MIN) ? 1.0 / sqrt(n2) : 0.0;
-        nrinv = (float)(-inv);
+        rescore = (float)(-inv);
 #pragma unroll
         for (int i = 0; i < TC_D; ++i) b[i] = finite ? (float)(-(double)c[i] * inv) : 0.0f;
     } else {
 #pragma unroll
         for (int i = 0; i < TC_D; ++i) b[i] = finite ? -2.0f * c[i] : 0.0f;
         double r = finite ? n2 : 0.0;
+        rescore = (float)r;
         npiece[0] = to_tf32((float)r); r -= (double)npiece[0];
         npiece[1] = to_tf32((float)r); r -= (double)npiece[1];
         npiece[2] = to_tf32((float)r);
@@ -278,14 +268,13 @@ __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ c
         hi[i] = to_tf32(b[i]);
         lo[i] = to_tf32(b[i] - hi[i]);
     }
-    // B' image: row j, 16-byte k-chunk q at (j/8)*768 + q*128 + (j%8)*16
-    float4* row = reinterpret_cast<float4*>(img + (j >> 3) * 768 + (j & 7) * 16);
+    // B' image: row j, 16-byte k-chunk q at (j/8)*BP_SBO + q*128 + (j%8)*16
+    float4* row = reinterpret_cast<float4*>(img + (j >> 3) * BP_SBO + (j & 7) * 16);
     row[0 * 8] = make_float4(hi[0], hi[1], hi[2], hi[3]);
     row[1 * 8] = make_float4(hi[4], hi[5], hi[6], hi[7]);
     row[2 * 8] = make_float4(lo[0], lo[1], lo[2], lo[3]);
     row[3 * 8] = make_float4(lo[4], lo[5], lo[6], lo[7]);
     row[4 * 8] = make_float4(npiece[0], npiece[1], npiece[2], 0.f);
-    row[5 * 8] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* raw = reinterpret_cast<float4*>(img + BP_BYTES + j * 32);
     raw[0] = make_float4(c[0], c[1], c[2], c[3]);
     raw[1] = make_float4(c[4], c[5], c[6], c[7]);
@@ -297,7 +286,7 @@ __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ c
         float nb = hsd_cosine_norm<TC_D>(ca, TC_D, tok);
         float2* aux = reinterpret_cast<float2*>(img + BP_BYTES + CB_BYTES + j * 8);
         *aux = make_float2(nb, __fsqrt_rn(nb));
-        reinterpret_cast<float*>(img + BP_BYTES + CB_BYTES + AUX_BYTES)[j] = nrinv;
+        reinterpret_cast<float*>(img + BP_BYTES + CB_BYTES + AUX_BYTES)[j] = rescore;
     }
     red[j] = (real && finite) ? (float)n2 : 0.0f;
     __syncthreads();
@@ -339,7 +328,10 @@ struct ExactEval {
     }
 };
 
+enum { ROLE_CTRL = 0, ROLE_SPLIT = 1, ROLE_RESOLVE = 2, ROLE_SCAN0 = 3, ROLE_SCAN1 = 4 };
+
 struct TcParams {
+    uint32_t role_map;          // 4 bits per warpgroup: the ROLE_* it plays
     const uint8_t* prep;        // [m] prepared images
     const SubInfo* sinfo;       // [m]
     const int* active;          // [m] 0/1 or nullptr (all active)
@@ -354,7 +346,6 @@ struct TcParams {
     int dbg_sub;
     unsigned long long* dbg_ts;   // DEBUG kernels only: [dbg_ts_units][8] SM-clock stamps of CTA 0's hand-offs (vqb_debug_tc_timeline)
     int dbg_ts_units;
-    uint32_t sleep_ns;            // back-off between polls of the roles that run ahead of / behind the critical path
 };
 
 __device__ __forceinline__ void store_code(void* codes, uint32_t code_bytes, size_t off, uint32_t v) {
@@ -366,38 +357,35 @@ __device__ __forceinline__ void store_code(void* codes, uint32_t code_bytes, siz
 // ----------------------------------------------------------------------------------- main kernel
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
-// minima of the four groups of four columns held by one x16 TMEM load
-__device__ __forceinline__ void group_min4(const uint32_t (&v)[16], float* g) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        g[q] = fminf(fmin3(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2])),
-                     __uint_as_float(v[4 * q + 3]));
-}
-
-// SKIP (timing experiments, VQB_TC_SKIP, cosine only; the codes are wrong): 1 = no resolve work, 2 = no scan post-phase
-template <int MK, bool DEBUG, int SKIP = 0>
+// Five warpgroups, roles assigned by p.role_map: control (TMA producer, MMA issuer) | splitter | resolve | scan columns 0-127 |
+// scan columns 128-255.
+// Both scan warpgroups drain EVERY accumulator, half the columns each, straight into registers (2 x tcgen05.ld.x64 per
+// thread) and release it as soon as the loads have landed: the accumulator is busy for one TMEM read latency instead of
+// a whole reduction, so the next MMA chain into it starts while its scores are still being reduced from registers.
+template <int MK, bool DEBUG>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wgrp = warp >> 2;
+    const int wgrp = warp >> 2, wq = warp & 3;
+    const int role = (int)((p.role_map >> (4 * wgrp)) & 15u);   // which role this warpgroup plays (ROLE_*)
     const int grp = blockIdx.x % p.n_groups, part = blockIdx.x / p.n_groups;
     const int s0 = grp * TC_G;
     const int g_cnt = min(TC_G, p.m - s0);
 
-    // barriers
+    // barriers (arrival counts are per WARP: a warp's lanes synchronise with __syncwarp, lane 0 arrives)
     const uint32_t bar0 = sbase + OFF_BAR;
-    constexpr int B_RAW_EMPTY = RAW_STAGES, B_A_FULL = 2 * RAW_STAGES, B_A_EMPTY = B_A_FULL + A_STAGES;
-    constexpr int B_ACC_FULL = B_A_EMPTY + A_STAGES, B_ACC_EMPTY = B_ACC_FULL + 2;
+    constexpr int B_RAW_EMPTY = RAW_STAGES, B_AT_FULL = 2 * RAW_STAGES, B_AT_EMPTY = B_AT_FULL + AT_STAGES;
+    constexpr int B_ACC_FULL = B_AT_EMPTY + AT_STAGES, B_ACC_EMPTY = B_ACC_FULL + 2;
     constexpr int B_MG_FULL = B_ACC_EMPTY + 2, B_MG_EMPTY = B_MG_FULL + MG_STAGES;
     constexpr int B_RES_FULL = B_MG_EMPTY + MG_STAGES, B_RES_EMPTY = B_RES_FULL + RES_STAGES;
     constexpr int B_COUNT = B_RES_EMPTY + RES_STAGES;
     static_assert(B_COUNT * 8 + 8 <= 512, "barrier area too small");
     auto RAW_FULL = [&](int i) { return bar0 + 8u * i; };
     auto RAW_EMPTY = [&](int i) { return bar0 + 8u * (B_RAW_EMPTY + i); };
-    auto A_FULL = [&](int i) { return bar0 + 8u * (B_A_FULL + i); };
-    auto A_EMPTY = [&](int i) { return bar0 + 8u * (B_A_EMPTY + i); };
+    auto AT_FULL = [&](int i) { return bar0 + 8u * (B_AT_FULL + i); };
+    auto AT_EMPTY = [&](int i) { return bar0 + 8u * (B_AT_EMPTY + i); };
     auto ACC_FULL = [&](int i) { return bar0 + 8u * (B_ACC_FULL + i); };
     auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (B_ACC_EMPTY + i); };
     auto MG_FULL = [&](int i) { return bar0 + 8u * (B_MG_FULL + i); };
@@ -405,6 +393,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
     auto RES_FULL = [&](int i) { return bar0 + 8u * (B_RES_FULL + i); };
     auto RES_EMPTY = [&](int i) { return bar0 + 8u * (B_RES_EMPTY + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 8 * B_COUNT);
+    // the warp's lanes have all finished what the arrival stands for; one arrival per warp
+    auto warp_arrive = [&](uint32_t bar) { __syncwarp(); if (lane == 0) mbar_arrive(bar); };
 
     // active subspaces of this group (same list for every role)
     uint32_t act_mask = 0;
@@ -428,6 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         for (int t = threadIdx.x; t < (int)(RINV_BYTES / 16); t += TC_THREADS)
             dri[t] = __ldg(src + (BP_BYTES + CB_BYTES + AUX_BYTES) / 16 + t);
     }
+    if (threadIdx.x < BP_PAD / 16) reinterpret_cast<float4*>(sm + OFF_BP + TC_G * BP_BYTES)[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = threadIdx.x; t < (int)(ONES_BYTES / 16); t += TC_THREADS) {
         // [16 groups][2 chunks][8 rows][16 B]: chunk 0 = (1,1,1,0), chunk 1 = 0
         const bool chunk0 = ((t >> 3) & 1) == 0;
@@ -438,16 +429,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         reinterpret_cast<float2*>(sm + OFF_SINFO)[threadIdx.x] = make_float2(sqrtf(si.cmax2) * 1.0000005f, si.unsafe ? 1.0f : 0.0f);
     }
     if (threadIdx.x == 0) {
-        // a raw tile is released by the splitter (128), every resolve unit (128 each) and the last MMA that read it (1)
-        for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(RAW_FULL(i), 1); mbar_init(RAW_EMPTY(i), 128 + 128 * n_act + 1); }
-        for (int i = 0; i < A_STAGES; ++i) { mbar_init(A_FULL(i), 128); mbar_init(A_EMPTY(i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 128); }
-        for (int i = 0; i < MG_STAGES; ++i) { mbar_init(MG_FULL(i), 128); mbar_init(MG_EMPTY(i), 128); }
-        for (int i = 0; i < RES_STAGES; ++i) { mbar_init(RES_FULL(i), 128); mbar_init(RES_EMPTY(i), 128); }
+        // a raw tile is released by the splitter (4 warps), the resolve warpgroup once per unit (4 warps each) and the
+        // last MMA that read it (1)
+        for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(RAW_FULL(i), 1); mbar_init(RAW_EMPTY(i), 4 + 4 * n_act + 1); }
+        for (int i = 0; i < AT_STAGES; ++i) { mbar_init(AT_FULL(i), 4); mbar_init(AT_EMPTY(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 8); }
+        for (int i = 0; i < MG_STAGES; ++i) { mbar_init(MG_FULL(i), 4); mbar_init(MG_EMPTY(i), 8 * n_act); }
+        for (int i = 0; i < RES_STAGES; ++i) { mbar_init(RES_FULL(i), 8); mbar_init(RES_EMPTY(i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();  // generic-proxy smem writes above -> visible to the tensor core / TMA
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (role == ROLE_CTRL && wq == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -455,88 +447,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
 
     const int my_tiles = (p.num_tiles - part + p.parts - 1) / p.parts;  // tiles part, part+parts, ...
 
-    if (wgrp == 0) {
+    if (role == ROLE_CTRL) {
         reg_dec<REGS_CTRL>();
-        if (warp == 0) {
+        if (wq == 0) {
             // ================================ TMA producer ================================
             if (lane == 0) {
                 for (int it = 0; it < my_tiles; ++it) {
                     const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-                    mbar_wait_relaxed(RAW_EMPTY(st), ph ^ 1, p.sleep_ns);
+                    mbar_wait<256>(RAW_EMPTY(st), ph ^ 1);
                     mbar_expect_tx(RAW_FULL(st), RAW_BYTES);
                     const int tile = part + it * p.parts;
                     tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));
                 }
             }
-        } else if (warp == 1) {
+        } else if (wq == 1) {
             // ================================ MMA issuer ==================================
-            if (lane == 0) {
-                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-                const uint64_t ones_desc = make_desc(sbase + OFF_ONES, 128, 256);
-                const bool use_norm = (MK != MK_COSINE) || (p.k < TC_N);
-                uint32_t u = 0;
-                for (int it = 0; it < my_tiles; ++it) {
-                    const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-                    mbar_wait(RAW_FULL(st), ph);   // TMA bytes have landed: the tensor core reads x_hi from the tile itself
-                    for (int i = 0; i < g_cnt; ++i) {
-                        if (!(act_mask >> i & 1)) continue;
-                        const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
-                        const int acc = u & 1, cph = (u >> 1) & 1;
-                        mbar_wait(ACC_EMPTY(acc), cph ^ 1);
-                        tc_fence_after();
+            // The whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers, so each
+            // tcgen05.mma is one instruction instead of a divergence loop); one elected lane issues.
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+            const uint64_t ones_desc = make_desc(sbase + OFF_ONES, 128, 256);
+            // descriptor bases; the 14-bit address field (bytes >> 4) never carries: every operand lies below 256 KB
+            const uint64_t raw_desc0 = make_desc_sw128(sbase + OFF_RAW), at_desc0 = make_desc_sw128(sbase + OFF_AT);
+            const uint64_t b_desc0 = make_desc(sbase + OFF_BP, 128, BP_SBO);
+            const bool use_norm = (MK != MK_COSINE) || (p.k < TC_N);
+            uint32_t u = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
+                const int at = it % AT_STAGES, atph = (it / AT_STAGES) & 1;
+                mbar_wait<64>(RAW_FULL(st), ph);   // TMA bytes have landed: the tensor core reads x_hi from the tile itself
+                mbar_wait<64>(AT_FULL(at), atph);  // x_lo tile (the splitter runs a tile ahead)
+                for (int i = 0; i < g_cnt; ++i) {
+                    if (!(act_mask >> i & 1)) continue;
+                    const int acc = u & 1, cph = (u >> 1) & 1;
+                    mbar_wait<32>(ACC_EMPTY(acc), cph ^ 1);
+                    tc_fence_after();
+                    const uint64_t xhi = raw_desc0 + (uint64_t)((st * RAW_BYTES + i * 32) >> 4);
+                    const uint64_t xlo = at_desc0 + (uint64_t)((at * RAW_BYTES + i * 32) >> 4);
+                    const uint64_t bhi = b_desc0 + (uint64_t)((i * BP_BYTES) >> 4);
+                    const uint32_t d = tmem_base + acc * TC_N;
+                    if (elect_one()) {
                         if (DEBUG && p.dbg_ts && blockIdx.x == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 0] = clock64();
-                        const uint64_t xhi = make_desc_sw128(sbase + OFF_RAW + st * RAW_BYTES + i * 32);
-                        const uint32_t a0 = sbase + OFF_AP + ast * AP_BYTES, b0 = sbase + OFF_BP + i * BP_BYTES;
-                        const uint32_t d = tmem_base + acc * TC_N;
-                        umma_tf32(d, xhi, make_desc(b0, 128, 768), idesc, 0);                                  // x_hi . c_hi
-                        umma_tf32(d, xhi, make_desc(b0 + 256, 128, 768), idesc, 1);                            // x_hi . c_lo
-                        if (use_norm) umma_tf32(d, ones_desc, make_desc(b0 + 512, 128, 768), idesc, 1);        // + ||c||^2
-                        mbar_wait(A_FULL(ast), aph);
-                        tc_fence_after();
-                        umma_tf32(d, make_desc(a0, 128, 256), make_desc(b0, 128, 768), idesc, 1);              // x_lo . c_hi
-                        umma_commit(A_EMPTY(ast));
+                        umma_tf32(d, xhi, bhi, idesc, 0);                                   // x_hi . c_hi
+                        umma_tf32(d, xhi, bhi + (256 >> 4), idesc, 1);                      // x_hi . c_lo
+                        if (use_norm) umma_tf32(d, ones_desc, bhi + (512 >> 4), idesc, 1);  // + ||c||^2
+                        umma_tf32(d, xlo, bhi, idesc, 1);                                   // x_lo . c_hi
                         umma_commit(ACC_FULL(acc));
-                        if (i == last_act) umma_commit(RAW_EMPTY(st));
+                        if (i == last_act) { umma_commit(AT_EMPTY(at)); umma_commit(RAW_EMPTY(st)); }
                         if (DEBUG && p.dbg_ts && blockIdx.x == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 1] = clock64();
-                        ++u;
                     }
+                    __syncwarp();
+                    ++u;
                 }
             }
         }
-    } else if (wgrp == 1) {
-        // ================================ splitter: x_lo + margin ======================
+    } else if (role == ROLE_SPLIT) {
+        // ================================ splitter: x_lo tile + margins, once per row tile ======================
         reg_dec<REGS_SPLIT>();
-        const int r = (warp - 4) * 32 + lane;  // tile row
+        const int r = wq * 32 + lane;  // tile row
+        const uint32_t r7 = (uint32_t)(r & 7);
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-            mbar_wait_relaxed(RAW_FULL(st), ph, p.sleep_ns);
+            const int at = it % AT_STAGES, atph = (it / AT_STAGES) & 1;
+            const int mg = it % MG_STAGES, mph = (it / MG_STAGES) & 1;
+            mbar_wait<128>(RAW_FULL(st), ph);
             const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
-            for (int i = 0; i < g_cnt; ++i) {
-                if (!(act_mask >> i & 1)) continue;
-                const int ast = u % A_STAGES, aph = (u / A_STAGES) & 1;
-                const int mg = u % MG_STAGES, mph = (u / MG_STAGES) & 1;
-                // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
-                const float4 v0 = *reinterpret_cast<const float4*>(rawrow + (((2 * i) ^ (r & 7)) << 4));
-                const float4 v1 = *reinterpret_cast<const float4*>(rawrow + (((2 * i + 1) ^ (r & 7)) << 4));
-                // x_lo = x - trunc_tf32(x): exact, and exactly what the tensor core leaves out when it reads x as tf32
-                float4 l0, l1;
-                l0.x = v0.x - __uint_as_float(__float_as_uint(v0.x) & 0xFFFFE000u);
-                l0.y = v0.y - __uint_as_float(__float_as_uint(v0.y) & 0xFFFFE000u);
-                l0.z = v0.z - __uint_as_float(__float_as_uint(v0.z) & 0xFFFFE000u);
-                l0.w = v0.w - __uint_as_float(__float_as_uint(v0.w) & 0xFFFFE000u);
-                l1.x = v1.x - __uint_as_float(__float_as_uint(v1.x) & 0xFFFFE000u);
-                l1.y = v1.y - __uint_as_float(__float_as_uint(v1.y) & 0xFFFFE000u);
-                l1.z = v1.z - __uint_as_float(__float_as_uint(v1.z) & 0xFFFFE000u);
-                l1.w = v1.w - __uint_as_float(__float_as_uint(v1.w) & 0xFFFFE000u);
-                mbar_wait_relaxed(A_EMPTY(ast), aph ^ 1, p.sleep_ns);
-                float4* dst = reinterpret_cast<float4*>(sm + OFF_AP + ast * AP_BYTES + (r >> 3) * 256 + (r & 7) * 16);
-                dst[0] = l0; dst[8] = l1;
-                fence_proxy_async();
-                mbar_arrive(A_FULL(ast));
-                if (DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 7] = clock64();
-                // this row's error margin M = KAPPA * S and indicator scale H = 2^(40 - floor(log2 S)):
-                // (th - g) * H >= 1 for every representable g < th in the score range, th * H far from overflow
+            uint8_t* atrow = sm + OFF_AT + at * RAW_BYTES + r * 128;
+            // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7); the x_lo tile keeps the same layout
+            float4 v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rawrow + ((c ^ r7) << 4));
+            mbar_wait<128>(AT_EMPTY(at), atph ^ 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(atrow + ((c ^ r7) << 4)) = make_float4(tf32_lo(v[c].x), tf32_lo(v[c].y), tf32_lo(v[c].z), tf32_lo(v[c].w));
+            fence_proxy_async();
+            warp_arrive(AT_FULL(at));
+            if (DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 7] = clock64();
+            u += n_act;
+            // every subspace's error margin M = KAPPA * S and indicator scale H = 2^(40 - floor(log2 S)):
+            // (th - g) * H >= 1 for every representable g < th in the score range, th * H far from overflow
+            float2 hm[TC_G];
+#pragma unroll
+            for (int i = 0; i < TC_G; ++i) {
+                const float4 v0 = v[2 * i], v1 = v[2 * i + 1];
                 float nx2 = 0.f;
                 nx2 = fmaf(v0.x, v0.x, nx2); nx2 = fmaf(v0.y, v0.y, nx2); nx2 = fmaf(v0.z, v0.z, nx2); nx2 = fmaf(v0.w, v0.w, nx2);
                 nx2 = fmaf(v1.x, v1.x, nx2); nx2 = fmaf(v1.y, v1.y, nx2); nx2 = fmaf(v1.z, v1.z, nx2); nx2 = fmaf(v1.w, v1.w, nx2);
@@ -549,93 +543,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 bool amb = (si.y != 0.f) || !(nx2 < 1e30f) || !(S > 1e-25f) || !(S < 1e30f);
                 if (MK == MK_COSINE) amb = amb || !(nx2 > 4.0f * FLT_MIN);
                 const uint32_t sexp = (__float_as_uint(S) >> 23) & 0xFFu;
-                const float H = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
-                const float M = amb ? -1.0f : KAPPA * S;
-                mbar_wait_relaxed(MG_EMPTY(mg), mph ^ 1, p.sleep_ns);
-                reinterpret_cast<float2*>(sm + OFF_MG + mg * MG_BYTES)[r] = make_float2(H, M);
-                mbar_arrive(MG_FULL(mg));
-                ++u;
+                hm[i].x = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
+                hm[i].y = amb ? -1.0f : KAPPA * S;
             }
-            mbar_arrive(RAW_EMPTY(st));
+            mbar_wait<128>(MG_EMPTY(mg), mph ^ 1);
+#pragma unroll
+            for (int i = 0; i < TC_G; ++i) reinterpret_cast<float2*>(sm + OFF_MG + mg * MG_BYTES)[i * TC_ROWS + r] = hm[i];
+            warp_arrive(MG_FULL(mg));
+            warp_arrive(RAW_EMPTY(st));
         }
-    } else if (wgrp < 4) {
+    } else if (role >= ROLE_SCAN0) {
         // ================================ scan ========================================
         reg_inc<REGS_SCAN>();
-        const int acc = wgrp - 2;                   // TMEM accumulator of this warpgroup
-        const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+        const int half = role - ROLE_SCAN0;         // column half of every accumulator this warpgroup drains
+        const int quarter = wq;                     // TMEM lane quarter this warp may read
         const int r = quarter * 32 + lane;          // tile row = TMEM lane
-        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 128;
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
+            const int mg = it % MG_STAGES, mph = (it / MG_STAGES) & 1;
             for (int i = 0; i < g_cnt; ++i) {
                 if (!(act_mask >> i & 1)) continue;
-                if ((int)(u & 1) != acc) { ++u; continue; }
-                const int cph = (u >> 1) & 1;
-                const int mg = u % MG_STAGES, mph = (u / MG_STAGES) & 1;
+                const int acc = u & 1, cph = (u >> 1) & 1;
                 const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
 
-                mbar_wait(ACC_FULL(acc), cph);
+                mbar_wait<32>(ACC_FULL(acc), cph);
                 tc_fence_after();
-                const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
+                const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && half == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 2] = clock64();
-                // ---- 256 scores -> 64 minima of four columns; the next x16 load is in flight while one is reduced
-                float gm[64];
-                uint32_t va[16], vb[16];
-                tmem_ld16(tcol, va);
-#pragma unroll
-                for (int c = 0; c < 16; c += 2) {
-                    tmem_ld_wait16(va);
-                    tmem_ld16(tcol + (c + 1) * 16, vb);
-                    if (DEBUG) {
-                        const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
-                        if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) p.dbg_scores[(size_t)row * TC_N + c * 16 + q] = __uint_as_float(va[q]);
-                        }
-                    }
-                    group_min4(va, &gm[4 * c]);
-                    tmem_ld_wait16(vb);
-                    if (c + 2 < 16) tmem_ld16(tcol + (c + 2) * 16, va);
-                    if (DEBUG) {
-                        const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
-                        if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) p.dbg_scores[(size_t)row * TC_N + (c + 1) * 16 + q] = __uint_as_float(vb[q]);
-                        }
-                    }
-                    group_min4(vb, &gm[4 * c + 4]);
-                }
+                // ---- this thread's 128 scores into registers, then the accumulator is free again
+                uint32_t v[128];
+                tmem_ld64(tlane + acc * TC_N, v);
+                tmem_ld64(tlane + acc * TC_N + 64, v + 64);
+                tmem_ld_wait128(v);
                 tc_fence_before();
-                mbar_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
+                warp_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 3] = clock64();
-
-                // ---- row minimum
-                float t1[22];
+                if (DEBUG) {
+                    const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
+                    if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
 #pragma unroll
-                for (int q = 0; q < 21; ++q) t1[q] = fmin3(gm[3 * q], gm[3 * q + 1], gm[3 * q + 2]);
-                t1[21] = gm[63];
-                float t2[8];
+                        for (int q = 0; q < 128; ++q) p.dbg_scores[(size_t)row * TC_N + half * 128 + q] = __uint_as_float(v[q]);
+                    }
+                }
+                // ---- 128 scores -> 32 minima of four columns -> minimum of the half row
+                float gm[32];
 #pragma unroll
-                for (int q = 0; q < 7; ++q) t2[q] = fmin3(t1[3 * q], t1[3 * q + 1], t1[3 * q + 2]);
-                t2[7] = t1[21];
-                const float mall = fmin3(fmin3(t2[0], t2[1], t2[2]), fmin3(t2[3], t2[4], t2[5]), fminf(t2[6], t2[7]));
+                for (int q = 0; q < 32; ++q)
+                    gm[q] = fminf(fmin3(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2])),
+                                  __uint_as_float(v[4 * q + 3]));
+                float t1[11];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) t1[q] = fmin3(gm[3 * q], gm[3 * q + 1], gm[3 * q + 2]);
+                t1[10] = fminf(gm[30], gm[31]);
+                const float hmin = fmin3(fmin3(t1[0], t1[1], t1[2]), fmin3(t1[3], t1[4], t1[5]),
+                                         fmin3(t1[6], t1[7], fmin3(t1[8], t1[9], t1[10])));
 
-                mbar_wait(MG_FULL(mg), mph);
-                const float2 hm = reinterpret_cast<const float2*>(sm + OFF_MG + mg * MG_BYTES)[r];
-                mbar_arrive(MG_EMPTY(mg));
+                mbar_wait<64>(MG_FULL(mg), mph);   // complete long before the first unit of the tile gets here
+                const float2 hm = reinterpret_cast<const float2*>(sm + OFF_MG + mg * MG_BYTES)[i * TC_ROWS + r];
+                warp_arrive(MG_EMPTY(mg));
                 const float H = hm.x, M = hm.y;
                 const float negH = -H;
-                const float thH = fmaf(mall, H, M * H);  // (mall + M) * H
+                const float thH = fmaf(hmin, H, M * H);  // (hmin + M) * H
 
-                // ---- groups within M of the minimum: indicator = sat((th - g) * H) in {0, 1}; the odd weights
+                // ---- groups within M of the half's minimum: indicator = sat((th - g) * H) in {0, 1}; the odd weights
                 // 129 + 2t make the sum decode to t iff exactly one group is flagged (two flagged groups sum to
-                // >= 258; a fractional indicator -- g within S * 2^-40 of the threshold -- cannot produce an odd
+                // >= 260; a fractional indicator -- g within S * 2^-40 of the threshold -- cannot produce an odd
                 // integer together with the always-full indicator of the minimum, and the resolve stage re-checks
-                // the decoded group against the row minimum anyway)
+                // the decoded group against the row minimum anyway).  The other half's minimum is compared with this
+                // one by the resolve stage.
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-                for (int t = 0; t < ((SKIP & 2) ? 0 : 64); ++t) {
+                for (int t = 0; t < 32; ++t) {
                     const float w = (float)(129 + 2 * t), ind = fsat_ind(gm[t], negH, thH);
                     if ((t & 3) == 0) a0 = fmaf(ind, w, a0);
                     if ((t & 3) == 1) a1 = fmaf(ind, w, a1);
@@ -644,91 +624,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 }
                 const float accw = (a0 + a1) + (a2 + a3);
                 const int wi = (int)accw;
-                const bool single = (M >= 0.f) && (accw >= 129.f) && (accw <= 255.f) && (accw == floorf(accw)) && (wi & 1);
+                const bool single = (M >= 0.f) && (accw >= 129.f) && (accw <= 191.f) && (accw == floorf(accw)) && (wi & 1);
                 // result word: the margin with its low six mantissa bits replaced by the group index; sign bit = ambiguous
                 const uint32_t word = single ? ((__float_as_uint(M) & ~63u) | (uint32_t)((wi - 129) >> 1)) : RES_AMBIGUOUS;
-                mbar_wait(RES_EMPTY(rs), rph ^ 1);
-                reinterpret_cast<float2*>(sm + OFF_RES + rs * RES_BYTES)[r] = make_float2(mall, __uint_as_float(word));
-                mbar_arrive(RES_FULL(rs));
+                mbar_wait<64>(RES_EMPTY(rs), rph ^ 1);
+                reinterpret_cast<float2*>(sm + OFF_RES + rs * RES_BYTES)[2 * r + half] = make_float2(hmin, __uint_as_float(word));
+                warp_arrive(RES_FULL(rs));
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 4] = clock64();
             }
         }
     } else {
         // ================================ resolve =====================================
         reg_dec<REGS_RESOLVE>();
-        const int par = wgrp - 4;                   // units of this parity
-        const int r = (warp & 3) * 32 + lane;       // tile row
+        const int r = wq * 32 + lane;               // tile row
+        const uint32_t r7 = (uint32_t)(r & 7);
         // lane-rotated candidate order: the eight lanes of a quarter-warp read eight different 16-byte
         // slots of their (arbitrary) 128-byte candidate groups -> conflict-free LDS.128 gathers
         const int h0 = lane & 1, rot = (lane >> 1) & 3;
+        const bool padded = p.k < TC_N;
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
             const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
             const bool live = row < p.n;
-            bool raw_seen = false;
+            mbar_wait<128>(RAW_FULL(st), ph);
+            const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
             for (int i = 0; i < g_cnt; ++i) {
                 if (!(act_mask >> i & 1)) continue;
-                if ((int)(u & 1) != par) { ++u; continue; }
                 const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
                 const int s = s0 + i;
-                if (!raw_seen) { mbar_wait_relaxed(RAW_FULL(st), ph, p.sleep_ns); raw_seen = true; }
                 // this row's sub-vector, halves in this lane's gather order
-                const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
-                const float4 xa = *reinterpret_cast<const float4*>(rawrow + (((2 * i + h0) ^ (r & 7)) << 4));
-                const float4 xb = *reinterpret_cast<const float4*>(rawrow + (((2 * i + (h0 ^ 1)) ^ (r & 7)) << 4));
-                mbar_wait_relaxed(RES_FULL(rs), rph, p.sleep_ns);
-                const float2 rv = reinterpret_cast<const float2*>(sm + OFF_RES + rs * RES_BYTES)[r];
-                mbar_arrive(RES_EMPTY(rs));
+                const float4 xa = *reinterpret_cast<const float4*>(rawrow + (((2 * i + h0) ^ r7) << 4));
+                const float4 xb = *reinterpret_cast<const float4*>(rawrow + (((2 * i + (h0 ^ 1)) ^ r7) << 4));
+                mbar_wait<64>(RES_FULL(rs), rph);
+                const float4 rv = reinterpret_cast<const float4*>(sm + OFF_RES + rs * RES_BYTES)[r];
+                warp_arrive(RES_EMPTY(rs));
                 const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 5] = clock64();
-                if (SKIP & 1) { mbar_arrive(RAW_EMPTY(st)); continue; }
-                const uint32_t word = __float_as_uint(rv.y);
+                // the half that holds the row minimum; the other half must stay clear of it by more than the margin
+                const bool sel = rv.z < rv.x;
+                const float ref = sel ? rv.z : rv.x, oth = sel ? rv.x : rv.z;
+                const uint32_t word = __float_as_uint(sel ? rv.w : rv.y);
                 const float* cb = reinterpret_cast<const float*>(sm + OFF_CB + i * CB_BYTES);
                 const float2* aux = reinterpret_cast<const float2*>(sm + OFF_AUX + i * AUX_BYTES);
                 uint32_t best = 0;
                 bool amb = true;
                 if (!(word & RES_AMBIGUOUS)) {
-                    const int t = (int)(word & 63u);
+                    // fp32 re-score of the four candidates in the tensor core's own form: -x.c/||c|| or ||c||^2 - 2 x.c
+                    const int t = (int)(word & 63u) + (sel ? 32 : 0);
                     const float M = __uint_as_float(word & ~63u);
                     const uint8_t* gbase = reinterpret_cast<const uint8_t*>(cb) + t * 128;
-                    const float* nri = reinterpret_cast<const float*>(sm + OFF_RINV + i * RINV_BYTES) + 4 * t;
-                    float b1 = __int_as_float(0x7f800000), b2 = b1;
-                    int jb = 0;
+                    const float* rsc = reinterpret_cast<const float*>(sm + OFF_RINV + i * RINV_BYTES) + 4 * t;
+                    float sc[4];
 #pragma unroll
                     for (int ii = 0; ii < 4; ++ii) {
                         const int q = (ii + rot) & 3;
                         const float4 ca = *reinterpret_cast<const float4*>(gbase + q * 32 + h0 * 16);
                         const float4 cc = *reinterpret_cast<const float4*>(gbase + q * 32 + (h0 ^ 1) * 16);
-                        float sc;
-                        if (MK == MK_COSINE) {
-                            float dot = ca.x * xa.x;
-                            dot = fmaf(ca.y, xa.y, dot); dot = fmaf(ca.z, xa.z, dot); dot = fmaf(ca.w, xa.w, dot);
-                            dot = fmaf(cc.x, xb.x, dot); dot = fmaf(cc.y, xb.y, dot); dot = fmaf(cc.z, xb.z, dot); dot = fmaf(cc.w, xb.w, dot);
-                            sc = dot * nri[q];
-                        } else {
-                            float e = ca.x - xa.x; sc = e * e;
-                            e = ca.y - xa.y; sc = fmaf(e, e, sc); e = ca.z - xa.z; sc = fmaf(e, e, sc); e = ca.w - xa.w; sc = fmaf(e, e, sc);
-                            e = cc.x - xb.x; sc = fmaf(e, e, sc); e = cc.y - xb.y; sc = fmaf(e, e, sc);
-                            e = cc.z - xb.z; sc = fmaf(e, e, sc); e = cc.w - xb.w; sc = fmaf(e, e, sc);
-                        }
-                        if (4 * t + q >= p.k) sc = __int_as_float(0x7f800000);  // padding slot
-                        b2 = fminf(b2, fmaxf(b1, sc));
-                        if (sc < b1) jb = q;
-                        b1 = fminf(b1, sc);
+                        float dot = ca.x * xa.x;
+                        dot = fmaf(ca.y, xa.y, dot); dot = fmaf(ca.z, xa.z, dot); dot = fmaf(ca.w, xa.w, dot);
+                        dot = fmaf(cc.x, xb.x, dot); dot = fmaf(cc.y, xb.y, dot); dot = fmaf(cc.z, xb.z, dot); dot = fmaf(cc.w, xb.w, dot);
+                        sc[ii] = (MK == MK_COSINE) ? dot * rsc[q] : fmaf(dot, -2.0f, rsc[q]);
+                        if (padded && 4 * t + q >= p.k) sc[ii] = __int_as_float(0x7f800000);  // padding slot
                     }
-                    float ref = rv.x;  // tensor-core row minimum: ||c||^2 - 2 x.c  (L2 kinds)  or  -x.c/||c||
-                    if (MK != MK_COSINE) {
-                        float nx2 = xa.x * xa.x;
-                        nx2 = fmaf(xa.y, xa.y, nx2); nx2 = fmaf(xa.z, xa.z, nx2); nx2 = fmaf(xa.w, xa.w, nx2);
-                        nx2 = fmaf(xb.x, xb.x, nx2); nx2 = fmaf(xb.y, xb.y, nx2); nx2 = fmaf(xb.z, xb.z, nx2); nx2 = fmaf(xb.w, xb.w, nx2);
-                        ref += nx2;
-                    }
-                    // accept iff this group really holds the row minimum and its best beats its runner-up by more than M
-                    const bool ok = (b1 - ref <= 0.5f * M) && (ref - b1 <= 0.5f * M) && (b2 - b1 > M);
+                    const float lo01 = fminf(sc[0], sc[1]), hi01 = fmaxf(sc[0], sc[1]);
+                    const float lo23 = fminf(sc[2], sc[3]), hi23 = fmaxf(sc[2], sc[3]);
+                    const float b1 = fminf(lo01, lo23);
+                    const float b2 = fmin3(hi01, hi23, fmaxf(lo01, lo23));
+                    const int ib = (lo01 <= lo23) ? ((sc[0] <= sc[1]) ? 0 : 1) : ((sc[2] <= sc[3]) ? 2 : 3);
+                    // accept iff this group really holds the row minimum, its best beats its runner-up by more than M
+                    // and no score of the other column half comes within M
+                    const bool ok = (fabsf(b1 - ref) <= 0.5f * M) && (b2 - b1 > M) && (oth - ref > M);
                     amb = !ok;
-                    best = (uint32_t)(4 * t + jb);
+                    best = (uint32_t)(4 * t + ((ib + rot) & 3));
                 }
                 // ---- everything else: the warp scans all k centroids of the row with the reference formula
                 uint32_t todo = __ballot_sync(0xFFFFFFFFu, amb && live);
@@ -766,22 +735,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 if (live) {
                     if (p.codes) store_code(p.codes, p.code_bytes, (size_t)row * p.stride_row + (size_t)s * p.stride_sub, best);
                     if (p.recon) {  // pq.rs:193-195: f16::from_f32 of the chosen centroid
-                        const float* c = cb + best * TC_D;
+                        const float4* c = reinterpret_cast<const float4*>(cb + best * TC_D);
+                        const float4 c0 = c[0], c1 = c[1];
                         __half2 h[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(c[2 * q], c[2 * q + 1]);
+                        h[0] = __floats2half2_rn(c0.x, c0.y); h[1] = __floats2half2_rn(c0.z, c0.w);
+                        h[2] = __floats2half2_rn(c1.x, c1.y); h[3] = __floats2half2_rn(c1.z, c1.w);
                         *reinterpret_cast<uint4*>(p.recon + (size_t)row * p.dim + (size_t)s * TC_D) = *reinterpret_cast<uint4*>(h);
                     }
                 }
-                mbar_arrive(RAW_EMPTY(st));
+                warp_arrive(RAW_EMPTY(st));
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 6] = clock64();
             }
-            // units of this tile that belong to the other resolve warpgroup count one arrival each there
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (role == ROLE_CTRL && wq == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // --------------------------------------------------------------------------------------- host
@@ -802,9 +771,12 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-template <int MK, bool DEBUG = false, int SKIP = 0>
+// timing variant selected by vqb_debug_tc_variant: the warpgroup -> role map (see vqb_tc_assign_launch)
+int g_tc_variant = 0;
+
+template <int MK, bool DEBUG = false>
 int launch_tc(vqb_ctx* ctx, const CUtensorMap& map, const TcParams& p, int grid) {
-    auto kern = k_tc_assign<MK, DEBUG, SKIP>;
+    auto kern = k_tc_assign<MK, DEBUG>;
     VQB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     kern<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(map, p);
     VQB_LAUNCHED(ctx);
@@ -863,19 +835,18 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
     p.code_bytes = code_bytes;
     p.dbg_scores = dbg_scores; p.dbg_stats = dbg_stats; p.dbg_sub = dbg_sub;
     p.dbg_ts = dbg_ts; p.dbg_ts_units = dbg_ts_units;
-    static const uint32_t sleep_ns = [] { const char* e = std::getenv("VQB_TC_SLEEP_NS"); long v = e ? std::atol(e) : -1; return (uint32_t)(v >= 0 ? v : 256); }();
-    p.sleep_ns = sleep_ns;
+    // warpgroup -> role.  The SM's warp arbiter prefers higher warp ids: the latency-critical MMA issuer sits highest.
+    static const uint32_t role_maps[4] = {
+        ROLE_SPLIT | ROLE_RESOLVE << 4 | ROLE_SCAN0 << 8 | ROLE_SCAN1 << 12 | ROLE_CTRL << 16,
+        ROLE_CTRL | ROLE_SPLIT << 4 | ROLE_RESOLVE << 8 | ROLE_SCAN0 << 12 | ROLE_SCAN1 << 16,
+        ROLE_SCAN0 | ROLE_SCAN1 << 4 | ROLE_SPLIT << 8 | ROLE_RESOLVE << 12 | ROLE_CTRL << 16,
+        ROLE_RESOLVE | ROLE_SPLIT << 4 | ROLE_CTRL << 8 | ROLE_SCAN0 << 12 | ROLE_SCAN1 << 16};
+    p.role_map = role_maps[g_tc_variant & 3];
     const int grid = p.n_groups * p.parts;
     if (dbg_scores || dbg_stats || dbg_ts) {
         if (mk == MK_COSINE) return launch_tc<MK_COSINE, true>(ctx, map, p, grid);
         if (mk == MK_TRAIN) return launch_tc<MK_TRAIN, true>(ctx, map, p, grid);
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for the training and cosine kinds only");
-    }
-    static const int skip = [] { const char* e = std::getenv("VQB_TC_SKIP"); return e ? std::atoi(e) : 0; }();
-    if (skip && mk == MK_COSINE) {
-        if (skip == 1) return launch_tc<MK_COSINE, false, 1>(ctx, map, p, grid);
-        if (skip == 2) return launch_tc<MK_COSINE, false, 2>(ctx, map, p, grid);
-        return launch_tc<MK_COSINE, false, 3>(ctx, map, p, grid);
     }
     switch (mk) {
         case MK_SQEUCLID: return launch_tc<MK_SQEUCLID>(ctx, map, p, grid);
@@ -884,6 +855,13 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
         case MK_TRAIN: return launch_tc<MK_TRAIN>(ctx, map, p, grid);
     }
     return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "metric kind %d has no tensor-core path", mk);
+}
+
+// Diagnostics: selects the warp-role order of the tensor kernel (0: scan warpgroups 2-3, 1: scan warpgroups 4-5).
+// Every variant produces the same codes; exists so that A/B timings need one build.
+extern "C" int vqb_debug_tc_variant(int order) {
+    g_tc_variant = order;
+    return VQB_SUCCESS;
 }
 
 extern "C" int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, size_t n, size_t dim, size_t m, size_t k,
