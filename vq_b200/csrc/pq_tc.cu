@@ -56,11 +56,11 @@ constexpr int RAW_STAGES = 3;      // TMA -> everyone: raw fp32 row tiles (128 r
 constexpr int AT_STAGES = 2;       // splitter -> MMA: x_lo tiles, same shape and swizzle as the raw tile
 constexpr int MG_STAGES = 2;       // splitter -> scan: margins of one row tile, [TC_G][128 rows]
 constexpr int RES_STAGES = 4;      // scan -> resolve: per-row candidate group of one unit
-constexpr int TC_THREADS = 640;    // 5 warpgroups: control | splitter | resolve | scan (columns 0-127) | scan (columns 128-255)
+constexpr int TC_THREADS = 640;    // 5 warpgroups: control | 2 helpers (split + resolve) | 2 scan (one per TMEM accumulator)
 // setmaxnreg budget: the pool is what the CTA was launched with (640 threads x 96 registers = 61440), so
-// 128*24 + 128*56 + 128*80 + 256*160 = 61440 must not exceed it or the last setmaxnreg.inc never returns
-constexpr int REGS_LAUNCH = 96, REGS_CTRL = 24, REGS_SPLIT = 56, REGS_SCAN = 160, REGS_RESOLVE = 80;
-static_assert(128 * REGS_CTRL + 128 * REGS_SPLIT + 256 * REGS_SCAN + 128 * REGS_RESOLVE <= TC_THREADS * REGS_LAUNCH,
+// 128*24 + 256*72 + 256*152 = 60416 must not exceed it or the last setmaxnreg.inc never returns
+constexpr int REGS_LAUNCH = 96, REGS_CTRL = 24, REGS_HELP = 72, REGS_SCAN = 152;
+static_assert(128 * REGS_CTRL + 256 * REGS_HELP + 256 * REGS_SCAN <= TC_THREADS * REGS_LAUNCH,
               "setmaxnreg budget exceeds the registers the CTA owns");
 
 constexpr uint32_t RAW_BYTES = TC_ROWS * 128;           // 16 KB per stage
@@ -74,7 +74,7 @@ constexpr uint32_t AUX_BYTES = TC_N * 8;                // 2 KB (nb, sb) per cen
 constexpr uint32_t RINV_BYTES = TC_N * 4;               // 1 KB per centroid: -1/||c|| (cosine) or ||c||^2 (L2 kinds), fp32 re-score
 constexpr uint32_t ONES_BYTES = 16 * 2 * 128;           // 4 KB: [16 row groups][2 k-chunks][8 rows][16 B]
 constexpr uint32_t MG_BYTES = TC_G * TC_ROWS * 8;       // float2 {H, M} per (subspace, row)
-constexpr uint32_t RES_BYTES = TC_ROWS * 16;            // per row: {half minimum, M | group index} of the two column halves
+constexpr uint32_t RES_BYTES = TC_ROWS * 8;             // float2 {row minimum, M | group index} per row
 constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES + RINV_BYTES;  // per-subspace prepared image in HBM
 
 constexpr uint32_t OFF_RAW = 0;
@@ -178,6 +178,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -328,7 +341,9 @@ struct ExactEval {
     }
 };
 
-enum { ROLE_CTRL = 0, ROLE_SPLIT = 1, ROLE_RESOLVE = 2, ROLE_SCAN0 = 3, ROLE_SCAN1 = 4 };
+// ROLE_HELP0/1: splitter of the even / odd row tiles and resolver of the even / odd units.  ROLE_SCAN0/1: scan of
+// TMEM accumulator 0 / 1 (= units of that parity).
+enum { ROLE_CTRL = 0, ROLE_HELP0 = 1, ROLE_HELP1 = 2, ROLE_SCAN0 = 3, ROLE_SCAN1 = 4 };
 
 struct TcParams {
     uint32_t role_map;          // 4 bits per warpgroup: the ROLE_* it plays
@@ -433,9 +448,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         // last MMA that read it (1)
         for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(RAW_FULL(i), 1); mbar_init(RAW_EMPTY(i), 4 + 4 * n_act + 1); }
         for (int i = 0; i < AT_STAGES; ++i) { mbar_init(AT_FULL(i), 4); mbar_init(AT_EMPTY(i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 8); }
-        for (int i = 0; i < MG_STAGES; ++i) { mbar_init(MG_FULL(i), 4); mbar_init(MG_EMPTY(i), 8 * n_act); }
-        for (int i = 0; i < RES_STAGES; ++i) { mbar_init(RES_FULL(i), 8); mbar_init(RES_EMPTY(i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 4); }
+        for (int i = 0; i < MG_STAGES; ++i) { mbar_init(MG_FULL(i), 4); mbar_init(MG_EMPTY(i), 4 * n_act); }
+        for (int i = 0; i < RES_STAGES; ++i) { mbar_init(RES_FULL(i), 4); mbar_init(RES_EMPTY(i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();  // generic-proxy smem writes above -> visible to the tensor core / TMA
@@ -500,16 +515,118 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 }
             }
         }
-    } else if (role == ROLE_SPLIT) {
-        // ================================ splitter: x_lo tile + margins, once per row tile ======================
-        reg_dec<REGS_SPLIT>();
-        const int r = wq * 32 + lane;  // tile row
-        const uint32_t r7 = (uint32_t)(r & 7);
+    } else if (role >= ROLE_SCAN0) {
+        // ================================ scan ========================================
+        reg_inc<REGS_SCAN>();
+        const int acc = role - ROLE_SCAN0;          // TMEM accumulator (= unit parity) this warpgroup drains, whole rows
+        const int quarter = wq;                     // TMEM lane quarter this warp may read
+        const int r = quarter * 32 + lane;          // tile row = TMEM lane
+        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N;
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
-            const int at = it % AT_STAGES, atph = (it / AT_STAGES) & 1;
             const int mg = it % MG_STAGES, mph = (it / MG_STAGES) & 1;
+            for (int i = 0; i < g_cnt; ++i) {
+                if (!(act_mask >> i & 1)) continue;
+                if ((int)(u & 1) != acc) { ++u; continue; }
+                const int cph = (u >> 1) & 1;
+                const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
+                ++u;
+
+                mbar_wait<32>(ACC_FULL(acc), cph);
+                tc_fence_after();
+                const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 2] = clock64();
+                // ---- 256 scores -> 64 minima of four columns; the next x32 load is in flight while one is reduced
+                float gm[64];
+                uint32_t va[32], vb[32];
+                auto dump = [&](const uint32_t (&v)[32], int c) {   // DEBUG only: raw scores of one subspace
+                    const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
+                    if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) p.dbg_scores[(size_t)row * TC_N + c * 32 + q] = __uint_as_float(v[q]);
+                    }
+                };
+                auto gmin8 = [&](const uint32_t (&v)[32], float* g) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        g[q] = fminf(fmin3(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2])),
+                                     __uint_as_float(v[4 * q + 3]));
+                };
+                tmem_ld32(tcol, va);
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    tmem_ld_wait32(va);
+                    tmem_ld32(tcol + (c + 1) * 32, vb);
+                    if (DEBUG) dump(va, c);
+                    gmin8(va, &gm[8 * c]);
+                    tmem_ld_wait32(vb);
+                    if (c + 2 < 8) tmem_ld32(tcol + (c + 2) * 32, va);
+                    if (DEBUG) dump(vb, c + 1);
+                    gmin8(vb, &gm[8 * c + 8]);
+                }
+                tc_fence_before();
+                warp_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 3] = clock64();
+
+                // ---- row minimum
+                float t1[22];
+#pragma unroll
+                for (int q = 0; q < 21; ++q) t1[q] = fmin3(gm[3 * q], gm[3 * q + 1], gm[3 * q + 2]);
+                t1[21] = gm[63];
+                float t2[8];
+#pragma unroll
+                for (int q = 0; q < 7; ++q) t2[q] = fmin3(t1[3 * q], t1[3 * q + 1], t1[3 * q + 2]);
+                t2[7] = t1[21];
+                const float mall = fmin3(fmin3(t2[0], t2[1], t2[2]), fmin3(t2[3], t2[4], t2[5]), fminf(t2[6], t2[7]));
+
+                mbar_wait<64>(MG_FULL(mg), mph);   // complete long before the first unit of the tile gets here
+                const float2 hm = reinterpret_cast<const float2*>(sm + OFF_MG + mg * MG_BYTES)[i * TC_ROWS + r];
+                warp_arrive(MG_EMPTY(mg));
+                const float H = hm.x, M = hm.y;
+                const float negH = -H;
+                const float thH = fmaf(mall, H, M * H);  // (mall + M) * H
+
+                // ---- groups within M of the minimum: indicator = sat((th - g) * H) in {0, 1}; the odd weights
+                // 129 + 2t make the sum decode to t iff exactly one group is flagged (two flagged groups sum to
+                // >= 260; a fractional indicator -- g within S * 2^-40 of the threshold -- cannot produce an odd
+                // integer together with the always-full indicator of the minimum, and the resolve stage re-checks
+                // the decoded group against the row minimum anyway)
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 64; ++t) {
+                    const float w = (float)(129 + 2 * t), ind = fsat_ind(gm[t], negH, thH);
+                    if ((t & 3) == 0) a0 = fmaf(ind, w, a0);
+                    if ((t & 3) == 1) a1 = fmaf(ind, w, a1);
+                    if ((t & 3) == 2) a2 = fmaf(ind, w, a2);
+                    if ((t & 3) == 3) a3 = fmaf(ind, w, a3);
+                }
+                const float accw = (a0 + a1) + (a2 + a3);
+                const int wi = (int)accw;
+                const bool single = (M >= 0.f) && (accw >= 129.f) && (accw <= 255.f) && (accw == floorf(accw)) && (wi & 1);
+                // result word: the margin with its low six mantissa bits replaced by the group index; sign bit = ambiguous
+                const uint32_t word = single ? ((__float_as_uint(M) & ~63u) | (uint32_t)((wi - 129) >> 1)) : RES_AMBIGUOUS;
+                mbar_wait<64>(RES_EMPTY(rs), rph ^ 1);
+                reinterpret_cast<float2*>(sm + OFF_RES + rs * RES_BYTES)[r] = make_float2(mall, __uint_as_float(word));
+                warp_arrive(RES_FULL(rs));
+                if (stamp) p.dbg_ts[(u - 1) * 8 + 4] = clock64();
+            }
+        }
+    } else {
+        // ================================ helpers: split the row tiles of one parity, resolve the units of one parity ======
+        reg_dec<REGS_HELP>();
+        const int par = role - ROLE_HELP0;
+        const int r = wq * 32 + lane;               // tile row
+        const uint32_t r7 = (uint32_t)(r & 7);
+        // lane-rotated candidate order: the eight lanes of a quarter-warp read eight different 16-byte
+        // slots of their (arbitrary) 128-byte candidate groups -> conflict-free LDS.128 gathers
+        const int h0 = lane & 1, rot = (lane >> 1) & 3;
+        const bool padded = p.k < TC_N;
+
+        // x_lo tile + margins of row tile `ts` (runs one tile ahead of the MMAs)
+        auto split_tile = [&](int ts) {
+            const int st = ts % RAW_STAGES, ph = (ts / RAW_STAGES) & 1;
+            const int at = ts % AT_STAGES, atph = (ts / AT_STAGES) & 1;
+            const int mg = ts % MG_STAGES, mph = (ts / MG_STAGES) & 1;
             mbar_wait<128>(RAW_FULL(st), ph);
             const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
             uint8_t* atrow = sm + OFF_AT + at * RAW_BYTES + r * 128;
@@ -523,8 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 *reinterpret_cast<float4*>(atrow + ((c ^ r7) << 4)) = make_float4(tf32_lo(v[c].x), tf32_lo(v[c].y), tf32_lo(v[c].z), tf32_lo(v[c].w));
             fence_proxy_async();
             warp_arrive(AT_FULL(at));
-            if (DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 7] = clock64();
-            u += n_act;
+            if (DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && ts * n_act < p.dbg_ts_units) p.dbg_ts[ts * n_act * 8 + 7] = clock64();
             // every subspace's error margin M = KAPPA * S and indicator scale H = 2^(40 - floor(log2 S)):
             // (th - g) * H >= 1 for every representable g < th in the score range, th * H far from overflow
             float2 hm[TC_G];
@@ -551,128 +667,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
             for (int i = 0; i < TC_G; ++i) reinterpret_cast<float2*>(sm + OFF_MG + mg * MG_BYTES)[i * TC_ROWS + r] = hm[i];
             warp_arrive(MG_FULL(mg));
             warp_arrive(RAW_EMPTY(st));
-        }
-    } else if (role >= ROLE_SCAN0) {
-        // ================================ scan ========================================
-        reg_inc<REGS_SCAN>();
-        const int half = role - ROLE_SCAN0;         // column half of every accumulator this warpgroup drains
-        const int quarter = wq;                     // TMEM lane quarter this warp may read
-        const int r = quarter * 32 + lane;          // tile row = TMEM lane
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 128;
+        };
+
+        if (par == 0) split_tile(0);
         uint32_t u = 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const int mg = it % MG_STAGES, mph = (it / MG_STAGES) & 1;
-            for (int i = 0; i < g_cnt; ++i) {
-                if (!(act_mask >> i & 1)) continue;
-                const int acc = u & 1, cph = (u >> 1) & 1;
-                const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
-                ++u;
-
-                mbar_wait<32>(ACC_FULL(acc), cph);
-                tc_fence_after();
-                const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && half == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
-                if (stamp) p.dbg_ts[(u - 1) * 8 + 2] = clock64();
-                // ---- this thread's 128 scores into registers, then the accumulator is free again
-                uint32_t v[128];
-                tmem_ld64(tlane + acc * TC_N, v);
-                tmem_ld64(tlane + acc * TC_N + 64, v + 64);
-                tmem_ld_wait128(v);
-                tc_fence_before();
-                warp_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
-                if (stamp) p.dbg_ts[(u - 1) * 8 + 3] = clock64();
-                if (DEBUG) {
-                    const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
-                    if (p.dbg_scores && s0 + i == p.dbg_sub && row < p.n) {
-#pragma unroll
-                        for (int q = 0; q < 128; ++q) p.dbg_scores[(size_t)row * TC_N + half * 128 + q] = __uint_as_float(v[q]);
-                    }
-                }
-                // ---- 128 scores -> 32 minima of four columns -> minimum of the half row
-                float gm[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    gm[q] = fminf(fmin3(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2])),
-                                  __uint_as_float(v[4 * q + 3]));
-                float t1[11];
-#pragma unroll
-                for (int q = 0; q < 10; ++q) t1[q] = fmin3(gm[3 * q], gm[3 * q + 1], gm[3 * q + 2]);
-                t1[10] = fminf(gm[30], gm[31]);
-                const float hmin = fmin3(fmin3(t1[0], t1[1], t1[2]), fmin3(t1[3], t1[4], t1[5]),
-                                         fmin3(t1[6], t1[7], fmin3(t1[8], t1[9], t1[10])));
-
-                mbar_wait<64>(MG_FULL(mg), mph);   // complete long before the first unit of the tile gets here
-                const float2 hm = reinterpret_cast<const float2*>(sm + OFF_MG + mg * MG_BYTES)[i * TC_ROWS + r];
-                warp_arrive(MG_EMPTY(mg));
-                const float H = hm.x, M = hm.y;
-                const float negH = -H;
-                const float thH = fmaf(hmin, H, M * H);  // (hmin + M) * H
-
-                // ---- groups within M of the half's minimum: indicator = sat((th - g) * H) in {0, 1}; the odd weights
-                // 129 + 2t make the sum decode to t iff exactly one group is flagged (two flagged groups sum to
-                // >= 260; a fractional indicator -- g within S * 2^-40 of the threshold -- cannot produce an odd
-                // integer together with the always-full indicator of the minimum, and the resolve stage re-checks
-                // the decoded group against the row minimum anyway).  The other half's minimum is compared with this
-                // one by the resolve stage.
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    const float w = (float)(129 + 2 * t), ind = fsat_ind(gm[t], negH, thH);
-                    if ((t & 3) == 0) a0 = fmaf(ind, w, a0);
-                    if ((t & 3) == 1) a1 = fmaf(ind, w, a1);
-                    if ((t & 3) == 2) a2 = fmaf(ind, w, a2);
-                    if ((t & 3) == 3) a3 = fmaf(ind, w, a3);
-                }
-                const float accw = (a0 + a1) + (a2 + a3);
-                const int wi = (int)accw;
-                const bool single = (M >= 0.f) && (accw >= 129.f) && (accw <= 191.f) && (accw == floorf(accw)) && (wi & 1);
-                // result word: the margin with its low six mantissa bits replaced by the group index; sign bit = ambiguous
-                const uint32_t word = single ? ((__float_as_uint(M) & ~63u) | (uint32_t)((wi - 129) >> 1)) : RES_AMBIGUOUS;
-                mbar_wait<64>(RES_EMPTY(rs), rph ^ 1);
-                reinterpret_cast<float2*>(sm + OFF_RES + rs * RES_BYTES)[2 * r + half] = make_float2(hmin, __uint_as_float(word));
-                warp_arrive(RES_FULL(rs));
-                if (stamp) p.dbg_ts[(u - 1) * 8 + 4] = clock64();
-            }
-        }
-    } else {
-        // ================================ resolve =====================================
-        reg_dec<REGS_RESOLVE>();
-        const int r = wq * 32 + lane;               // tile row
-        const uint32_t r7 = (uint32_t)(r & 7);
-        // lane-rotated candidate order: the eight lanes of a quarter-warp read eight different 16-byte
-        // slots of their (arbitrary) 128-byte candidate groups -> conflict-free LDS.128 gathers
-        const int h0 = lane & 1, rot = (lane >> 1) & 3;
-        const bool padded = p.k < TC_N;
-        uint32_t u = 0;
-        for (int it = 0; it < my_tiles; ++it) {
+            if (it + 1 < my_tiles && ((it + 1) & 1) == par) split_tile(it + 1);
             const int st = it % RAW_STAGES, ph = (it / RAW_STAGES) & 1;
             const unsigned long long row = (unsigned long long)(part + it * p.parts) * TC_ROWS + r;
             const bool live = row < p.n;
-            mbar_wait<128>(RAW_FULL(st), ph);
+            bool raw_seen = false;
             const uint8_t* rawrow = sm + OFF_RAW + st * RAW_BYTES + r * 128;
             for (int i = 0; i < g_cnt; ++i) {
                 if (!(act_mask >> i & 1)) continue;
+                if ((int)(u & 1) != par) { ++u; continue; }
                 const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
+                if (!raw_seen) { mbar_wait<128>(RAW_FULL(st), ph); raw_seen = true; }
                 const int s = s0 + i;
                 // this row's sub-vector, halves in this lane's gather order
                 const float4 xa = *reinterpret_cast<const float4*>(rawrow + (((2 * i + h0) ^ r7) << 4));
                 const float4 xb = *reinterpret_cast<const float4*>(rawrow + (((2 * i + (h0 ^ 1)) ^ r7) << 4));
                 mbar_wait<64>(RES_FULL(rs), rph);
-                const float4 rv = reinterpret_cast<const float4*>(sm + OFF_RES + rs * RES_BYTES)[r];
+                const float2 rv = reinterpret_cast<const float2*>(sm + OFF_RES + rs * RES_BYTES)[r];
                 warp_arrive(RES_EMPTY(rs));
                 const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 5] = clock64();
-                // the half that holds the row minimum; the other half must stay clear of it by more than the margin
-                const bool sel = rv.z < rv.x;
-                const float ref = sel ? rv.z : rv.x, oth = sel ? rv.x : rv.z;
-                const uint32_t word = __float_as_uint(sel ? rv.w : rv.y);
+                const float ref = rv.x;
+                const uint32_t word = __float_as_uint(rv.y);
                 const float* cb = reinterpret_cast<const float*>(sm + OFF_CB + i * CB_BYTES);
                 const float2* aux = reinterpret_cast<const float2*>(sm + OFF_AUX + i * AUX_BYTES);
                 uint32_t best = 0;
                 bool amb = true;
                 if (!(word & RES_AMBIGUOUS)) {
                     // fp32 re-score of the four candidates in the tensor core's own form: -x.c/||c|| or ||c||^2 - 2 x.c
-                    const int t = (int)(word & 63u) + (sel ? 32 : 0);
+                    const int t = (int)(word & 63u);
                     const float M = __uint_as_float(word & ~63u);
                     const uint8_t* gbase = reinterpret_cast<const uint8_t*>(cb) + t * 128;
                     const float* rsc = reinterpret_cast<const float*>(sm + OFF_RINV + i * RINV_BYTES) + 4 * t;
@@ -693,9 +722,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     const float b1 = fminf(lo01, lo23);
                     const float b2 = fmin3(hi01, hi23, fmaxf(lo01, lo23));
                     const int ib = (lo01 <= lo23) ? ((sc[0] <= sc[1]) ? 0 : 1) : ((sc[2] <= sc[3]) ? 2 : 3);
-                    // accept iff this group really holds the row minimum, its best beats its runner-up by more than M
-                    // and no score of the other column half comes within M
-                    const bool ok = (fabsf(b1 - ref) <= 0.5f * M) && (b2 - b1 > M) && (oth - ref > M);
+                    // accept iff this group really holds the row minimum and its best beats its runner-up by more than M
+                    const bool ok = (fabsf(b1 - ref) <= 0.5f * M) && (b2 - b1 > M);
                     amb = !ok;
                     best = (uint32_t)(4 * t + ((ib + rot) & 3));
                 }
@@ -772,7 +800,7 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 // timing variant selected by vqb_debug_tc_variant: the warpgroup -> role map (see vqb_tc_assign_launch)
-int g_tc_variant = 0;
+int g_tc_variant = 1;
 
 template <int MK, bool DEBUG = false>
 int launch_tc(vqb_ctx* ctx, const CUtensorMap& map, const TcParams& p, int grid) {
@@ -837,10 +865,10 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
     p.dbg_ts = dbg_ts; p.dbg_ts_units = dbg_ts_units;
     // warpgroup -> role.  The SM's warp arbiter prefers higher warp ids: the latency-critical MMA issuer sits highest.
     static const uint32_t role_maps[4] = {
-        ROLE_SPLIT | ROLE_RESOLVE << 4 | ROLE_SCAN0 << 8 | ROLE_SCAN1 << 12 | ROLE_CTRL << 16,
-        ROLE_CTRL | ROLE_SPLIT << 4 | ROLE_RESOLVE << 8 | ROLE_SCAN0 << 12 | ROLE_SCAN1 << 16,
-        ROLE_SCAN0 | ROLE_SCAN1 << 4 | ROLE_SPLIT << 8 | ROLE_RESOLVE << 12 | ROLE_CTRL << 16,
-        ROLE_RESOLVE | ROLE_SPLIT << 4 | ROLE_CTRL << 8 | ROLE_SCAN0 << 12 | ROLE_SCAN1 << 16};
+        ROLE_HELP0 | ROLE_HELP1 << 4 | ROLE_SCAN0 << 8 | ROLE_SCAN1 << 12 | ROLE_CTRL << 16,
+        ROLE_CTRL | ROLE_HELP0 << 4 | ROLE_HELP1 << 8 | ROLE_SCAN0 << 12 | ROLE_SCAN1 << 16,
+        ROLE_SCAN0 | ROLE_SCAN1 << 4 | ROLE_HELP0 << 8 | ROLE_HELP1 << 12 | ROLE_CTRL << 16,
+        ROLE_HELP0 | ROLE_SCAN0 << 4 | ROLE_CTRL << 8 | ROLE_SCAN1 << 12 | ROLE_HELP1 << 16};
     p.role_map = role_maps[g_tc_variant & 3];
     const int grid = p.n_groups * p.parts;
     if (dbg_scores || dbg_stats || dbg_ts) {
