@@ -81,6 +81,21 @@ int vqb_host_alloc(vqb_ctx* ctx, size_t bytes, void** hptr);   /* pinned */
 int vqb_host_free(vqb_ctx* ctx, void* hptr);
 int vqb_memcpy(vqb_ctx* ctx, void* dst, const void* src, size_t bytes); /* any direction, blocking */
 
+/* ======================= multi-GPU: one process per GPU ======================
+ * PQ training shards the rows over the GPUs of a box and exchanges ONE fused buffer
+ * [sums | count_lo | count_hi] per k-means iteration (src/core/vector.rs:432-447 over row shards); encode, BQ, SQ and TSVQ
+ * encode shard rows with no collective.  The library owns the NCCL communicator (libnccl.so.2 is opened at run time, so
+ * a single-GPU host needs no NCCL): rank 0 calls vqb_comm_unique_id, ships the VQB_COMM_ID_BYTES to the other ranks by
+ * any means (MPI, a file, torch.distributed), every rank calls vqb_comm_init_rank (collective), then trains with
+ * vqb_train_opts.flags = VQB_TRAIN_USE_COMM, row_offset and n_global. */
+#define VQB_COMM_ID_BYTES 128
+int vqb_comm_unique_id(void* id_out /* VQB_COMM_ID_BYTES */);
+int vqb_comm_init_rank(vqb_ctx* ctx, const void* id, int rank, int world);
+int vqb_comm_destroy(vqb_ctx* ctx);
+int vqb_comm_info(vqb_ctx* ctx, int* rank, int* world);
+/* In-place float sum of a device buffer over the communicator's ranks, enqueued on the context stream. */
+int vqb_comm_allreduce(vqb_ctx* ctx, float* buf, size_t count);
+
 /* ======================= Distance ============================================ */
 
 /* Distance::compute (src/core/distance.rs:48-65) for `rows` independent pairs:
@@ -123,19 +138,22 @@ typedef uint64_t (*vqb_reseed_fn)(void* user, uint32_t subspace);
 typedef int (*vqb_allreduce_fn)(void* user, float* buf, size_t count, void* cuda_stream);
 
 #define VQB_UPDATE_ORDERED 0 /* per-cluster sums in ascending row order == vector.rs:368-384, bit-exact */
-#define VQB_UPDATE_FAST    1 /* fixed-shape segmented sums: deterministic, not the reference's order */
+#define VQB_UPDATE_FAST    1 /* fixed-shape partial sums (one pass over X, no second copy): deterministic, not the reference's order */
 #define VQB_ASSIGN_AUTO    0
 #define VQB_ASSIGN_EXACT   1 /* CUDA-core kernel evaluating the reference's formula for every centroid */
 #define VQB_ASSIGN_TENSOR  2 /* tcgen05 GEMM-form scores + exact re-check of the candidates */
+
+#define VQB_TRAIN_USE_COMM 1u /* flags: rows are sharded over the ranks of the context's communicator (vqb_comm_init_rank);
+                                 the per-iteration exchange is one ncclAllReduce issued by the library on the context stream */
 
 typedef struct vqb_train_opts {
     uint32_t struct_size;        /* sizeof(vqb_train_opts) */
     uint32_t update_mode;        /* VQB_UPDATE_*  */
     uint32_t assign_mode;        /* VQB_ASSIGN_*  */
-    uint32_t reserved;
+    uint32_t flags;              /* VQB_TRAIN_*  */
     vqb_reseed_fn reseed;        /* may be NULL: empty clusters then keep their centroid */
     void* reseed_user;
-    vqb_allreduce_fn allreduce;  /* NULL: single GPU */
+    vqb_allreduce_fn allreduce;  /* NULL: single GPU, or the context's own communicator with VQB_TRAIN_USE_COMM */
     void* allreduce_user;
     uint64_t row_offset;         /* global id of this rank's first row (0 on a single GPU) */
     uint64_t n_global;           /* total rows over all ranks (0: == n) */

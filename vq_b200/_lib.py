@@ -17,6 +17,8 @@ ERR_UNSUPPORTED_DEVICE, ERR_DIM_MISMATCH, FAILURE = -4, -5, -99
 METRIC_IDS = {"squared_euclidean": 0, "euclidean": 1, "manhattan": 2, "cosine": 3}
 UPDATE_ORDERED, UPDATE_FAST = 0, 1
 ASSIGN_AUTO, ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1, 2
+TRAIN_USE_COMM = 1
+COMM_ID_BYTES = 128
 
 RESEED_FN = C.CFUNCTYPE(C.c_uint64, C.c_void_p, C.c_uint32)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -25,7 +27,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 class TrainOpts(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("update_mode", C.c_uint32), ("assign_mode", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
         ("reseed", RESEED_FN), ("reseed_user", C.c_void_p),
         ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p),
         ("row_offset", C.c_uint64), ("n_global", C.c_uint64),
@@ -50,6 +52,11 @@ SIGNATURES = {
     "vqb_host_alloc": (C.c_int, [_P, _SZ, C.POINTER(_P)]),
     "vqb_host_free": (C.c_int, [_P, _P]),
     "vqb_memcpy": (C.c_int, [_P, _P, _P, _SZ]),
+    "vqb_comm_unique_id": (C.c_int, [_P]),
+    "vqb_comm_init_rank": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "vqb_comm_destroy": (C.c_int, [_P]),
+    "vqb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vqb_comm_allreduce": (C.c_int, [_P, _P, _SZ]),
     "vqb_distance_batch": (C.c_int, [_P, C.c_int, _P, _P, _SZ, _SZ, _P]),
     "vqb_bq_quantize": (C.c_int, [_P, _P, _SZ, C.c_float, C.c_uint8, C.c_uint8, _P]),
     "vqb_bq_dequantize": (C.c_int, [_P, _P, _SZ, C.c_uint8, C.c_uint8, _P]),

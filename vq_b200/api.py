@@ -16,6 +16,7 @@ import ctypes as C
 import math
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -56,6 +57,9 @@ class FfiError(VqError):
 
 
 # --------------------------------------------------------------------------- engine
+_live_engines = weakref.WeakSet()   # every open Engine: CUDA-tensor arguments are ordered against their streams
+
+
 class Engine:
     """One vqb_ctx: a GPU, its streams and scratch memory."""
 
@@ -72,6 +76,7 @@ class Engine:
             raise RuntimeError(f"vqb_ctx_create failed ({rc})")
         self.h = h
         self.device = device
+        _live_engines.add(self)
 
     def close(self):
         if getattr(self, "h", None):
@@ -148,15 +153,41 @@ def _is_torch(a):
     return torch is not None and isinstance(a, torch.Tensor)
 
 
+def _torch_dtype(dtype, signed_alias=False):
+    """numpy dtype -> torch dtype, looked up lazily (torch.uint16 / uint32 exist from torch 2.3 on)."""
+    name = {np.float32: "float32", np.uint8: "uint8", np.float16: "float16", np.int32: "int32",
+            np.uint16: "int16" if signed_alias else "uint16", np.uint32: "int32" if signed_alias else "uint32"}[dtype]
+    return getattr(torch, name)
+
+
+def _order_after_torch(t):
+    """The engine launches on its own stream: make it wait for whatever torch has queued for this tensor (and for the
+    caching allocator's previous users of its memory) on torch's current stream.  Every call that takes CUDA tensors
+    synchronises the engine before it returns (_sync_if_torch / blocking training calls), so temporaries made here are
+    never recycled while an engine kernel still reads them."""
+    if not t.is_cuda:
+        return
+    cur = torch.cuda.current_stream(t.device)
+    for e in list(_live_engines):
+        if e.h and e.device == t.device.index:
+            es = torch.cuda.ExternalStream(e.stream, device=t.device)
+            if es.cuda_stream != cur.cuda_stream:
+                es.wait_stream(cur)
+
+
 def _in(a, dtype):
     """-> (pointer, keepalive, on_cuda). numpy arrays are made contiguous; torch tensors pass zero-copy."""
     if _is_torch(a):
-        tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.float16: torch.float16,
-               np.uint16: torch.uint16, np.uint32: torch.uint32, np.int32: torch.int32}[dtype]
+        tdt = _torch_dtype(dtype)
         t = a.detach()
         if t.dtype != tdt:
-            t = t.to(tdt)
+            # same-width signed integers (what _out_like hands out for u16 / u32 codes) are reinterpreted, not converted
+            if dtype in (np.uint16, np.uint32) and t.dtype == _torch_dtype(dtype, signed_alias=True):
+                t = t.contiguous().view(tdt)
+            else:
+                t = t.to(tdt)
         t = t.contiguous()
+        _order_after_torch(t)
         return C.c_void_p(t.data_ptr()), t, t.is_cuda
     arr = np.ascontiguousarray(a, dtype=dtype)
     return C.c_void_p(arr.ctypes.data), arr, False
@@ -165,9 +196,8 @@ def _in(a, dtype):
 def _out_like(src, shape, dtype):
     """Output buffer on the same side as `src`."""
     if _is_torch(src) and src.is_cuda:
-        tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.float16: torch.float16,
-               np.uint16: torch.int16, np.uint32: torch.int32}[dtype]
-        t = torch.empty(tuple(shape), dtype=tdt, device=src.device)
+        t = torch.empty(tuple(shape), dtype=_torch_dtype(dtype, signed_alias=True), device=src.device)
+        _order_after_torch(t)
         return C.c_void_p(t.data_ptr()), t
     arr = np.empty(shape, dtype=dtype)
     return C.c_void_p(arr.ctypes.data), arr
@@ -401,8 +431,11 @@ class ProductQuantizer:
         self._allreduce_cb = None
         if dist is not None:
             opts.row_offset, opts.n_global = dist.row_offset, dist.n_global
-            self._allreduce_cb = dist.allreduce_callback()
-            opts.allreduce = self._allreduce_cb
+            if getattr(dist, "use_comm", False):   # the engine's own NCCL communicator (vq_b200.dist.init_comm)
+                opts.flags = _lib.TRAIN_USE_COMM
+            else:
+                self._allreduce_cb = dist.allreduce_callback()
+                opts.allreduce = self._allreduce_cb
         px, keep, _ = _in(training_data, np.float32)
         cb = np.empty((m, k, self._sub_dim), np.float32)
         iters = np.zeros(m, np.uint32)

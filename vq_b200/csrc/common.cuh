@@ -193,18 +193,23 @@ inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int vqb_pq_assign_exact_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n, size_t dim,
                                size_t m, size_t k, size_t sub_dim, const float* codebooks,
                                const int* sub_list_dev, int n_sub, void* codes, uint32_t code_bytes,
-                               size_t code_stride_row, size_t code_stride_sub, __half* recon);
+                               size_t code_stride_row, size_t code_stride_sub, __half* recon,
+                               const int* n_sub_dev = nullptr, const uint32_t* go = nullptr);
 
 // tensor-core (tcgen05) GEMM-form assignment, pq_tc.cu.  `prep` is a device workspace of
 // vqb_tc_prep_bytes(m) bytes filled by vqb_tc_prepare from the current codebooks.
 size_t vqb_tc_prep_bytes(size_t m);
 bool vqb_tc_supported(int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k, size_t sub_dim);
-int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t m, size_t k, void* prep);
+int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t m, size_t k, void* prep,
+                   const uint32_t* go = nullptr);
+// the 2-D tensor map over a row-major f32 matrix x[n, dim] used by the TMA-fed kernels: box = 32 floats x 128 rows, SWIZZLE_128B
+struct CUtensorMap_st;
+int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out);
 int vqb_tc_assign_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k,
                          const void* prep, const int* active_dev, void* codes, uint32_t code_bytes,
                          size_t code_stride_row, size_t code_stride_sub, __half* recon,
                          float* dbg_scores = nullptr, unsigned long long* dbg_stats = nullptr, int dbg_sub = 0,
-                         unsigned long long* dbg_ts = nullptr, int dbg_ts_units = 0);
+                         unsigned long long* dbg_ts = nullptr, int dbg_ts_units = 0, const uint32_t* go = nullptr);
 // rows below which VQB_ASSIGN_AUTO keeps the CUDA-core kernel (the tensor kernel stages 128 KB of
 // codebooks per CTA before its first tile)
 constexpr size_t VQB_TC_MIN_ROWS = 1024;

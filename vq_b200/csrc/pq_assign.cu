@@ -39,8 +39,12 @@ __global__ void __launch_bounds__(AS_THREADS)
 k_assign_exact(const float* __restrict__ x, size_t n, int dim, int k, int sub_dim_rt,
                const float* __restrict__ codebooks, const int* __restrict__ sub_list, int k_chunk,
                void* __restrict__ codes, uint32_t code_bytes, size_t stride_row, size_t stride_sub,
-               __half* __restrict__ recon) {
+               __half* __restrict__ recon, const int* __restrict__ n_sub_dev, const uint32_t* __restrict__ go) {
     extern __shared__ __align__(16) float smem[];
+    // training loop gating (pq_train.cu): a speculatively enqueued iteration is a no-op unless the previous one allowed
+    // it, and the list of still-active subspaces lives on the device
+    if (go && *go == 0) return;
+    if (n_sub_dev && (int)blockIdx.y >= *n_sub_dev) return;
     const int d = D > 0 ? D : sub_dim_rt;
     const int s = sub_list ? sub_list[blockIdx.y] : (int)blockIdx.y;
     const size_t row = (size_t)blockIdx.x * AS_THREADS + threadIdx.x;
@@ -126,7 +130,7 @@ k_assign_exact(const float* __restrict__ x, size_t n, int dim, int k, int sub_di
 template <int MK>
 int launch_mk(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t k, size_t d, const float* cb,
               const int* sub_list, int n_sub, void* codes, uint32_t code_bytes, size_t stride_row,
-              size_t stride_sub, __half* recon) {
+              size_t stride_sub, __half* recon, const int* n_sub_dev, const uint32_t* go) {
     // centroid chunk that fits a 96 KB dynamic smem budget
     size_t per = d * sizeof(float) + (MK == MK_COSINE ? sizeof(CosAux) : 0);
     if (per == 0) per = 4;
@@ -140,7 +144,7 @@ int launch_mk(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t k, size
         auto kern = k_assign_exact<MK, DD>;                                                                \
         VQB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, AS_THREADS, smem, ctx->stream>>>(x, n, (int)dim, (int)k, (int)d, cb, sub_list, k_chunk, \
-                                                     codes, code_bytes, stride_row, stride_sub, recon);    \
+                                                     codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go); \
         break;                                                                                             \
     }
     switch (d) {
@@ -153,7 +157,7 @@ int launch_mk(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t k, size
             auto kern = k_assign_exact<MK, 0>;
             VQB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<grid, AS_THREADS, smem, ctx->stream>>>(x, n, (int)dim, (int)k, (int)d, cb, sub_list, k_chunk,
-                                                         codes, code_bytes, stride_row, stride_sub, recon);
+                                                         codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
         }
     }
 #undef VQB_AS_CASE
@@ -165,16 +169,17 @@ int launch_mk(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t k, size
 
 int vqb_pq_assign_exact_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t dim, size_t m, size_t k,
                                size_t d, const float* cb, const int* sub_list, int n_sub, void* codes,
-                               uint32_t code_bytes, size_t stride_row, size_t stride_sub, __half* recon) {
+                               uint32_t code_bytes, size_t stride_row, size_t stride_sub, __half* recon,
+                               const int* n_sub_dev, const uint32_t* go) {
     (void)m;
     if (n == 0 || n_sub == 0) return VQB_SUCCESS;
     if (dim > (size_t)INT32_MAX || k > (size_t)INT32_MAX) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "shape too large");
     switch (mk) {
-        case MK_SQEUCLID: return launch_mk<MK_SQEUCLID>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon);
-        case MK_EUCLID: return launch_mk<MK_EUCLID>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon);
-        case MK_MANHATTAN: return launch_mk<MK_MANHATTAN>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon);
-        case MK_COSINE: return launch_mk<MK_COSINE>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon);
-        case MK_TRAIN: return launch_mk<MK_TRAIN>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon);
+        case MK_SQEUCLID: return launch_mk<MK_SQEUCLID>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
+        case MK_EUCLID: return launch_mk<MK_EUCLID>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
+        case MK_MANHATTAN: return launch_mk<MK_MANHATTAN>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
+        case MK_COSINE: return launch_mk<MK_COSINE>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
+        case MK_TRAIN: return launch_mk<MK_TRAIN>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
     }
     return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric kind %d", mk);
 }

@@ -237,9 +237,10 @@ __device__ __forceinline__ float tf32_lo(float v) {  // v - trunc_tf32(v): exact
 // [c_hi | c_lo | norm pieces] in its shared-memory image, a raw f32 copy and the cosine norms.
 template <int MK>
 __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ codebooks, int k, uint8_t* __restrict__ prep,
-                                                      SubInfo* __restrict__ sinfo) {
+                                                      SubInfo* __restrict__ sinfo, const uint32_t* __restrict__ go) {
     __shared__ float red[TC_N];
     __shared__ uint32_t bad;
+    if (go && *go == 0) return;
     const int s = blockIdx.x, j = threadIdx.x;
     if (j == 0) bad = 0;
     __syncthreads();
@@ -347,6 +348,7 @@ enum { ROLE_CTRL = 0, ROLE_HELP0 = 1, ROLE_HELP1 = 2, ROLE_SCAN0 = 3, ROLE_SCAN1
 
 struct TcParams {
     uint32_t role_map;          // 4 bits per warpgroup: the ROLE_* it plays
+    const uint32_t* go;         // training loop: the launch is a no-op when *go == 0 (speculatively enqueued iteration)
     const uint8_t* prep;        // [m] prepared images
     const SubInfo* sinfo;       // [m]
     const int* active;          // [m] 0/1 or nullptr (all active)
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
     // the warp's lanes have all finished what the arrival stands for; one arrival per warp
     auto warp_arrive = [&](uint32_t bar) { __syncwarp(); if (lane == 0) mbar_arrive(bar); };
 
+    if (p.go && *p.go == 0) return;
     // active subspaces of this group (same list for every role)
     uint32_t act_mask = 0;
     for (int i = 0; i < g_cnt; ++i)
@@ -813,6 +816,20 @@ int launch_tc(vqb_ctx* ctx, const CUtensorMap& map, const TcParams& p, int grid)
 
 }  // namespace
 
+int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled is not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VQB_SUCCESS;
+}
+
 size_t vqb_tc_prep_bytes(size_t m) { return m * (size_t)PREP_BYTES + m * sizeof(SubInfo) + 256; }
 
 bool vqb_tc_supported(int mk, const float* x, size_t n, size_t dim, size_t m, size_t k, size_t d) {
@@ -824,11 +841,11 @@ bool vqb_tc_supported(int mk, const float* x, size_t n, size_t dim, size_t m, si
     return get_encode_fn() != nullptr;
 }
 
-int vqb_tc_prepare(vqb_ctx* ctx, int mk, const float* codebooks, size_t m, size_t k, void* prep) {
+int vqb_tc_prepare(vqb_ctx* ctx, int mk, const float* codebooks, size_t m, size_t k, void* prep, const uint32_t* go) {
     uint8_t* img = static_cast<uint8_t*>(prep);
     SubInfo* sinfo = reinterpret_cast<SubInfo*>(img + ((m * (size_t)PREP_BYTES + 255) & ~(size_t)255));
-    if (mk == MK_COSINE) k_tc_prepare<MK_COSINE><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo);
-    else k_tc_prepare<MK_TRAIN><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo);
+    if (mk == MK_COSINE) k_tc_prepare<MK_COSINE><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo, go);
+    else k_tc_prepare<MK_TRAIN><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo, go);
     VQB_LAUNCHED(ctx);
     return VQB_SUCCESS;
 }
@@ -836,20 +853,12 @@ int vqb_tc_prepare(vqb_ctx* ctx, int mk, const float* codebooks, size_t m, size_
 int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t dim, size_t m, size_t k, const void* prep,
                          const int* active_dev, void* codes, uint32_t code_bytes, size_t stride_row, size_t stride_sub,
                          __half* recon, float* dbg_scores, unsigned long long* dbg_stats, int dbg_sub,
-                         unsigned long long* dbg_ts, int dbg_ts_units) {
+                         unsigned long long* dbg_ts, int dbg_ts_units, const uint32_t* go) {
     if (n == 0) return VQB_SUCCESS;
-    PFN_encodeTiled enc = get_encode_fn();
-    if (!enc) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled is not available");
     CUtensorMap map;
-    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n};
-    cuuint64_t gstr[1] = {(cuuint64_t)dim * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    VQB_TRY(vqb_make_x_tensormap(ctx, x, n, dim, &map));
     TcParams p;
+    p.go = go;
     const uint8_t* img = static_cast<const uint8_t*>(prep);
     p.prep = img;
     p.sinfo = reinterpret_cast<const SubInfo*>(img + ((m * (size_t)PREP_BYTES + 255) & ~(size_t)255));

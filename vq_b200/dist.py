@@ -62,19 +62,36 @@ def pointer_is_cuda(ptr: int) -> bool:
         return True  # engine buffers are device memory whenever a GPU is present
 
 
+def init_comm(engine, group=None):
+    """Gives `engine` the library-owned NCCL communicator (include/vqb200.h, multi-GPU section): rank 0 draws the
+    128-byte id, torch.distributed carries it to the other ranks (any transport would do), every rank joins.
+    Afterwards RowShard(..., use_comm=True) trains with the all-reduce issued by the library itself -- no Python in
+    the loop."""
+    rank, world = td.get_rank(group), td.get_world_size(group)
+    buf = (C.c_char * _lib.COMM_ID_BYTES)()
+    if rank == 0:
+        engine.check(engine.lib.vqb_comm_unique_id(buf))
+    box = [bytes(buf.raw)]
+    td.broadcast_object_list(box, src=td.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = (C.c_char * _lib.COMM_ID_BYTES).from_buffer_copy(box[0])
+    engine.check(engine.lib.vqb_comm_init_rank(engine.h, ident, rank, world))
+    return rank, world
+
+
 @dataclass
 class RowShard:
     """This rank's share of a row-sharded training set."""
     row_offset: int
     n_global: int
     group: object = None  # torch.distributed process group (None = default group)
+    use_comm: bool = False  # True: the engine's own communicator (init_comm) instead of the torch.distributed callback
 
     @classmethod
-    def for_rank(cls, n_global: int, rank: int | None = None, world: int | None = None, group=None):
+    def for_rank(cls, n_global: int, rank: int | None = None, world: int | None = None, group=None, use_comm: bool = False):
         rank = td.get_rank(group) if rank is None else rank
         world = td.get_world_size(group) if world is None else world
         b, _ = shard_bounds(n_global, rank, world)
-        return cls(b, n_global, group)
+        return cls(b, n_global, group, use_comm)
 
     def all_reduce_pointer(self, ptr: int, count: int, stream: int | None, cuda: bool | None = None) -> int:
         if count == 0:
