@@ -33,7 +33,8 @@ sys.path.insert(0, ROOT)
 N_ROWS, DIM, M, K = 1_000_000, 768, 96, 256
 ENC_METRIC = "cosine"           # configs[2]: L2 k-means training (src/core/vector.rs:352-363) + cosine encode
 TRAIN_ITERS_FOR_CODEBOOK = 3
-NCU_DRAM_BYTES_PER_LAUNCH = 3_075_748_000 + 98_195_200   # read + written, 1M x 768 cosine encode (profiles/r01c_*)
+NCU_RAW_CSV = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_tc_assign_ncu_raw.csv")
+EPILOGUE_CYCLES_PER_UNIT = 576.5    # profiles/r02_ubench.txt (E): scan of one 128-row x 256-centroid unit, 8 warps, nothing else on the SM
 METRIC_NAME = "pq_encode_throughput"
 UNIT = "Mvec/s"
 
@@ -55,6 +56,23 @@ def parse():
     p.add_argument("--no-clock-probe", action="store_true", help="skip the 0.7 s untimed continuation (profiler runs)")
     p.add_argument("--no-paths", action="store_true", help="skip the per-path throughputs (BQ/SQ, Manhattan, L2 kinds, TSVQ)")
     return p.parse_args()
+
+
+def ncu_dram_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_tc_assign<cosine> launch (1M x 768), read from the committed
+    `ncu --set full` raw page; None when the file is not there."""
+    try:
+        import csv
+        rows = list(csv.reader(open(NCU_RAW_CSV)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(vals[i].replace(",", "")) * scale[units[i]]
+        return int(tot)
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -322,8 +340,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC_NAME, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"PQ encode {args.rows}x{DIM} f32, m={M}, k={K}, {args.metric}", "rows_per_gpu": args.rows,
-                   "dim": DIM, "m": M, "k": K, "distance": args.metric},
+        "config": {"workload": f"PQ encode {args.rows}x{DIM} f32 per GPU, m={M}, k={K}, {args.metric}", "rows_per_gpu": args.rows,
+                   "dim": DIM, "m": M, "k": K, "distance": args.metric, "assign": args.assign,
+                   "l2": "input (3.07 GB) > L2 (126 MB)", "parallelism": f"rows sharded over {args.gpus} GPU(s), no collective",
+                   "rows_timed_per_step": rows},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -397,7 +417,6 @@ def main():
         step_device()
     torch.cuda.synchronize()
     clk = clocks.stop()
-    clk["note"] = "nvidia-smi -lms 50 from warm-up through the timed steps and a 0.7 s untimed continuation of the same step"
     if dist_on:
         t = torch.tensor([ms], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX); ms = float(t.item())
     ms_per_step = ms / args.steps
@@ -408,17 +427,17 @@ def main():
     flops = 2.0 * rows * DIM * K                       # 2*n*dim*k per pass
     hbm_bytes = rows * DIM * 4 + rows * M              # X read once + u8 codes written
     tf = flops / kern_s / 1e12
+    # third bound: the CUDA-core scan of the 256 scores of every (row, subspace) pair, from the
+    # scan-only micro-benchmark: cycles per (128-row tile, subspace) unit and SM at the maximum SM clock
+    units_per_sm = (rows / 128.0) * M / 148.0
+    epi_floor_s = units_per_sm * EPILOGUE_CYCLES_PER_UNIT / 1.965e9
     roofline = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": tf / peaks["bf16_tflops"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH if rows == N_ROWS else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_tc_assign<cosine>, one launch, "
-                                  "profiles/r01c_tc_assign_ncu_raw.csv (ncu --set full); algorithmic bytes = "
-                                  f"{rows * DIM * 4 + rows * M}",
+                "frac": tf / peaks["bf16_tflops"], "traffic": ncu_dram_bytes() if rows == N_ROWS else None,
                 "peak_source": peaks["source"],
-                "note": "tf32-kind contraction (3 MMAs of K=8 per 128x256 tile) scored against the measured dense bf16 peak "
-                        "(tf32 nominal = half); at sub_dim 8 the MMA -> TMEM drain -> MMA cycle of an accumulator paces "
-                        "the kernel, not the tensor pipe (DESIGN.md 3.1, tools/tc_timeline.py)",
                 "hbm": {"achieved": hbm_bytes / kern_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": hbm_bytes / kern_s / 1e9 / peaks["hbm_gbs"]}}
+                        "frac": hbm_bytes / kern_s / 1e9 / peaks["hbm_gbs"]},
+                "epilogue": {"floor_ms": epi_floor_s * 1e3, "frac": epi_floor_s / kern_s,
+                             "note": "scan-only floor, profiles/r02_ubench.txt (E)"}}
 
     out = {
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -426,8 +445,8 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"PQ encode {rows}x{DIM} f32 per GPU, m={M}, k={K}, {args.metric}", "rows_per_gpu": rows,
                    "dim": DIM, "m": M, "k": K, "distance": args.metric, "assign": args.assign,
-                   "l2": "input batch (3.07 GB) is larger than L2 (126 MB): no reuse between timed iterations",
-                   "parallelism": f"rows sharded over {world} GPU(s), no collective"},
+                   "l2": "input (3.07 GB) > L2 (126 MB)", "parallelism": f"rows sharded over {world} GPU(s), no collective",
+                   "rows_timed_per_step": rows},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
     }
 
@@ -454,28 +473,47 @@ def main():
                 t = torch.tensor([dt], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX); dt = float(t.item())
             out["e2e"] = {"value": world * e_rows * n_e2e / dt / 1e6, "unit": UNIT,
                           "h2d_bytes_per_step": int(e_rows * DIM * 4), "d2h_bytes_per_step": int(e_rows * DIM * 2),
-                          "note": "pinned host f32 in, reference-format f16 reconstruction out; chunked 3-stream pipeline"}
+                          "note": "pinned f32 in, f16 reconstruction out, 3-stream chunks"}
             del hx, hr
         except Exception as ex:  # never lose the primary line
             out["e2e"] = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
 
-    # ---- k-means iterations/s on the same batch (row-sharded; one all-reduce per iteration) ----
+    # ---- k-means iterations/s: BASELINE config 3 = ONE fixed 1M x 768 training set, rows sharded over the N GPUs
+    # (strong scaling), one fused all-reduce per iteration issued by the library's own NCCL communicator ----
     if args.kmeans_iters > 0:
         try:
             import ctypes as C
             from vq_b200 import _lib
-            shard = RowShard(row_offset=rank * rows, n_global=world * rows) if dist_on else None
+            from vq_b200.dist import init_comm, shard_bounds
+            n_total = rows
+            if dist_on:
+                init_comm(eng)
+                r0, r1 = shard_bounds(n_total, rank, world)
+                # every rank draws the same training set (seed of rank 0's encode batch) and keeps its row range
+                g0 = torch.Generator(device="cuda"); g0.manual_seed(20240)
+                c0 = torch.randn(1024, DIM, device="cuda", generator=g0)
+                xk = torch.empty(r1 - r0, DIM, device="cuda")
+                for a0 in range(0, n_total, 131072):
+                    a1 = min(n_total, a0 + 131072)
+                    ids = torch.randint(0, 1024, (a1 - a0,), device="cuda", generator=g0)
+                    blk = c0[ids] + 0.25 * torch.randn(a1 - a0, DIM, device="cuda", generator=g0)
+                    lo, hi = max(a0, r0), min(a1, r1)
+                    if lo < hi:
+                        xk[lo - r0:hi - r0] = blk[lo - a0:hi - a0]
+                del blk, c0
+            else:
+                r0, r1, xk = 0, n_total, x
+            n_loc = r1 - r0
             opts = _lib.TrainOpts(); opts.struct_size = C.sizeof(_lib.TrainOpts); opts.update_mode = _lib.UPDATE_FAST
-            keep = None
-            if shard is not None:
-                keep = shard.allreduce_callback(); opts.allreduce = keep
-                opts.row_offset, opts.n_global = shard.row_offset, shard.n_global
+            if dist_on:
+                opts.flags = _lib.TRAIN_USE_COMM
+                opts.row_offset, opts.n_global = r0, n_total
             cb = np.empty((M, K, DIM // M), np.float32); it_run = np.zeros(M, np.uint32)
-            ginit, _ = vq.draw_init_indices(world * rows, M, K, 42)
+            ginit, _ = vq.draw_init_indices(n_total, M, K, 42)
             ginit = np.ascontiguousarray(ginit.reshape(-1))
 
             def train(iters):
-                eng.check(eng.lib.vqb_pq_train(eng.h, x.data_ptr(), rows, DIM, M, K, iters, ginit.ctypes.data,
+                eng.check(eng.lib.vqb_pq_train(eng.h, xk.data_ptr(), n_loc, DIM, M, K, iters, ginit.ctypes.data,
                                                C.byref(opts), cb.ctypes.data, it_run.ctypes.data))
             full_iters = args.kmeans_iters
             iter_ms = (C.c_float * full_iters)()
@@ -485,9 +523,7 @@ def main():
                 barrier()
                 t0 = time.perf_counter(); train(iters); torch.cuda.synchronize()
                 return time.perf_counter() - t0
-            wall(2)                                        # warm: allocator, kernels resident
-            # one 25-iteration training call (BASELINE metric): wall time with set-up, and the device time of
-            # every iteration from CUDA events on the engine stream (vqb_train_opts.iter_ms)
+            wall(2)                                        # warm: workspace slab, kernels resident, NCCL channels
             t_full, per_iter = None, None
             for _ in range(2):
                 t = wall(full_iters)
@@ -497,34 +533,43 @@ def main():
             if dist_on:
                 t = torch.tensor([per_iter, t_full], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX)
                 per_iter, t_full = float(t[0].item()), float(t[1].item())
+            # the iteration reads X twice (assignment, update) and writes / reads the codes once
+            km_bytes = 2.0 * n_total * DIM * 4 + 2.0 * n_total * M
+            km_tf = 2.0 * n_total * DIM * K / per_iter / 1e12 / world
             out["kmeans"] = {"value": ran / t_full, "unit": "iter/s", "ms_per_iter": per_iter * 1e3,
-                             "train_call_ms": t_full * 1e3, "iters_requested": full_iters, "iters_run_min": ran,
-                             "rows_total": world * rows, "iters_timed": ran, "update": "fast",
-                             "note": f"value = iterations run / wall time of ONE vqb_pq_train call ({full_iters} iterations requested, "
-                                     "workspace set-up and the one-time subspace-major copy included); ms_per_iter = median device "
-                                     "time of an iteration (CUDA events on the engine stream, vqb_train_opts.iter_ms); all 96 "
-                                     "subspaces advance per iteration; rows sharded, one fused all-reduce per iteration"}
+                             "train_call_ms": t_full * 1e3, "overhead_ms": (t_full - ran * per_iter) * 1e3,
+                             "iters": ran, "rows_total": n_total, "rows_per_gpu": n_loc, "scaling": "strong", "update": "fast",
+                             "collective": "ncclAllReduce by the library, 0.98 MB per iteration" if dist_on else "none",
+                             "roofline": {"bound": "hbm", "achieved": km_bytes / per_iter / 1e9 / world, "peak": peaks["hbm_gbs"],
+                                          "unit": "GB/s", "frac": km_bytes / per_iter / 1e9 / world / peaks["hbm_gbs"],
+                                          "tensor_frac": km_tf / peaks["bf16_tflops"]}}
+            if dist_on:
+                del xk
         except Exception as ex:
             out["kmeans"] = {"value": None, "unit": "iter/s", "error": repr(ex)[:200]}
 
     # ---- every other path of SURVEY 8(a) at 1 GPU, each against the roofline that bounds it ----
     if world == 1 and not args.no_paths:
         try:
-            out["paths"] = measure_paths(eng, ext, x, pq, peaks)
+            paths = measure_paths(eng, ext, x, pq, peaks)
         except Exception as ex:
-            out["paths"] = {"error": repr(ex)[:300]}
+            paths = {"error": repr(ex)[:300]}
+        # its own JSON line BEFORE the headline line (which stays short enough for the driver's tail)
+        print(json.dumps({"paths": paths, "note": "device-resident throughput of the other hot-path rows, N = 1"}), flush=True)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample) ----
     if rank == 0 and world == 1 and args.cpu_sample > 0:
         try:
             v, cores, kind, dt, backend = cpu_encode_rate(args.cpu_sample, args.metric)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                   "sample": f"{args.cpu_sample} of {rows} vectors ({dt:.1f} s); restated src/pq.rs:167-199 "
-                                             f"loop parallel over vectors; {backend}"}
+                                   "sample": f"{args.cpu_sample} of {rows} vectors ({dt:.1f} s), src/pq.rs:167-199 loop over all cores, {backend}"}
             try:
-                out["cpu_baseline"]["as_shipped"] = cpu_as_shipped(args.metric)
+                shipped = cpu_as_shipped(args.metric)
+                print(json.dumps({"cpu_as_shipped": shipped}), flush=True)   # separate line: the reference's own parallelism
+                out["cpu_baseline"]["kmeans_iter_per_s"] = shipped["kmeans"]["value"]
+                out["cpu_baseline"]["encode_1thread"] = shipped["encode_single_thread"]["value"]
             except Exception as ex:
-                out["cpu_baseline"]["as_shipped"] = {"error": repr(ex)[:200]}
+                out["cpu_baseline"]["as_shipped_error"] = repr(ex)[:100]
         except Exception as ex:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": repr(ex)[:200]}
 

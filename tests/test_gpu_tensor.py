@@ -220,3 +220,51 @@ def test_full_size_properties_1Mx768(vq):
     rec = l2.decode(l2.encode(x))
     mse = float(((rec - x) ** 2).mean())
     assert np.isfinite(mse) and mse < 0.5 * float(x.var())
+
+
+def test_tensor_adversarial_magnitudes_equals_exact(vq, eng):
+    """The margin M = KAPPA * S is argued from S = (||x|| + max||c||)^2 (or ||x|| for cosine): stress exactly the cases
+    that argument leans on -- magnitudes that differ by orders INSIDE a sub-vector, a codebook whose largest norm dwarfs
+    the typical one, rows far smaller / larger than every centroid, and centroid pairs separated by a few ulps.  The
+    pruned (tensor) route must still return the exact route's codes for the training distance and every encode metric."""
+    rng = np.random.default_rng(4242)
+    n, dim, m, k = 24_000, 32, 4, 256
+    x = mixture(n, dim, 99)
+    # magnitudes spread over 6 decades inside each sub-vector
+    x[:8000] *= np.exp(rng.uniform(np.log(1e-3), np.log(1e3), (8000, dim))).astype(F)
+    # rows that are tiny / huge against the codebook
+    x[8000:9000] *= F(1e-4)
+    x[9000:10000] *= F(3e3)
+    cb = sample_codebooks(x[10000:], m, k, 5)
+    cb[0, 17] *= F(2e3)                      # one centroid with a norm 2000 x the typical one: S is dominated by it
+    cb[1, 3] = cb[1, 2] * F(1.0 + 2 ** -22)  # near-duplicates: distances differ by a few ulps
+    cb[1, 5] = np.nextafter(cb[1, 4], F(np.inf))
+    cb[2, 40:48] *= np.exp(rng.uniform(np.log(1e-3), np.log(1e3), (8, 8))).astype(F)
+    cb[3, 0] = 0.0
+    # rows sitting (almost) on the near-duplicate pairs
+    x[10:20, 8:16] = cb[1, 2] * F(1.0 + 2 ** -23)
+    x[20:30, 8:16] = (cb[1, 4].astype(np.float64) * 0.5 + cb[1, 5].astype(np.float64) * 0.5).astype(F)
+    assert np.array_equal(assign_train(eng, x, cb, 2), assign_train(eng, x, cb, 1))
+    for metric in ("squared_euclidean", "euclidean", "cosine"):
+        pq = vq.ProductQuantizer.from_codebooks(cb, vq.Distance(metric))
+        c_t, r_t = pq.encode_with_recon(x, assign="tensor")
+        c_e, r_e = pq.encode_with_recon(x, assign="exact")
+        assert np.array_equal(c_t, c_e), metric
+        assert np.array_equal(r_t.view(np.uint16), r_e.view(np.uint16)), metric
+    # and the raw tensor scores stay inside the margin on this data too
+    d = dim // m
+    for sub, cosine in ((0, False), (2, False), (0, True), (2, True)):
+        got, rescans, _ = debug_scores(eng, x, cb, sub, cosine=cosine)
+        xs = x[:, sub * d:(sub + 1) * d].astype(np.float64)
+        c = cb[sub].astype(np.float64)
+        nc = np.sqrt((c * c).sum(1))
+        if cosine:
+            want = -(xs @ (c / np.where(nc > 0, nc, 1.0)[:, None]).T)
+            S = np.sqrt((xs * xs).sum(1))
+        else:
+            want = (c * c).sum(1)[None, :] - 2.0 * xs @ c.T
+            S = (np.sqrt((xs * xs).sum(1)) + nc.max()) ** 2
+        ok = S > 0
+        err = (np.abs(got - want).max(1)[ok] / S[ok]).max()
+        print(f"adversarial sub={sub} cosine={cosine}: max err/S = {err:.3e}, re-scanned pairs = {rescans}")
+        assert err <= KAPPA / 8

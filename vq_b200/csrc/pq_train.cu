@@ -448,6 +448,7 @@ k_epilogue(int m, int k, int* __restrict__ is_active, int* __restrict__ sub_list
             if (pos < (uint32_t)STATUS_CAP) { status[8 + 2 * pos] = (uint32_t)s; status[9 + 2 * pos] = (uint32_t)(idx - s * k); }
         }
     }
+    __syncthreads();   // every reader of the active flags is done before they are overwritten
     for (int s = threadIdx.x; s < m; s += blockDim.x) {
         int keep = 0;
         if (still[s]) {
