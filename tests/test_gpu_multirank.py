@@ -8,6 +8,7 @@ box has fewer than two GPUs.  The worker checks, on the CUDA path:
     (row-sharded sums cannot be bit-exact with a sequential f32 sum);
   * iteration counts agree, empty-cluster re-seeding across ranks included (a row owned by the other rank)."""
 import os
+import signal
 import subprocess
 import sys
 
@@ -30,8 +31,16 @@ def _gpu_count():
 def test_row_sharded_training_two_ranks(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "check_row_shard.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=800)
-    sys.stdout.write(r.stdout[-3000:])
-    sys.stderr.write(r.stderr[-3000:])
-    assert r.returncode == 0
-    assert "ROW-SHARD OK" in r.stdout
+    # own process group + hard deadline: a rank that fails leaves its peer waiting inside a collective
+    proc = subprocess.Popen(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=420)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        sys.stdout.write(out[-3000:]); sys.stderr.write(err[-3000:])
+        pytest.fail("row-shard check did not finish in 420 s (a rank failed or hung)")
+    sys.stdout.write(out[-3000:])
+    sys.stderr.write(err[-3000:])
+    assert proc.returncode == 0
+    assert "ROW-SHARD OK" in out

@@ -28,22 +28,27 @@ def same_on_all_ranks(cb):
 for (n, dim, m, k, iters, update, seed) in [(60_000, 64, 8, 256, 6, "fast", 11), (20_001, 48, 3, 64, 5, "ordered", 12),
                                             (9_000, 32, 4, 300, 4, "fast", 13)]:
     rng = np.random.default_rng(seed)                      # same data on every rank
-    centers = rng.standard_normal((128, dim)).astype(np.float32)
-    x = (centers[rng.integers(0, 128, n)] + 0.25 * rng.standard_normal((n, dim))).astype(np.float32)
+    centers = rng.standard_normal((1024, dim)).astype(np.float32)   # SURVEY 8d's separated mixture: k-means stays well conditioned
+    x = (centers[rng.integers(0, 1024, n)] + 0.25 * rng.standard_normal((n, dim))).astype(np.float32)
     init, _ = vq.draw_init_indices(n, m, k, 42)
     init[0, 1] = init[0, 0]                                # duplicate seed row -> an empty cluster -> re-seeding
     reseed_row = n - 7                                      # owned by the last rank
     b, e = shard_bounds(n, rank, world)
     xs = torch.from_numpy(x[b:e]).cuda()
+    dbg = lambda msg: print(f"[rank {rank}] n={n} {update}: {msg}", flush=True) if os.environ.get("ROW_SHARD_VERBOSE") else None
+    dbg("start")
     lib = vq.ProductQuantizer(xs, m, k, iters, vq.Distance.euclidean(), engine=eng, init_idx=init, update=update,
                               reseed=lambda s: reseed_row, dist=RowShard.for_rank(n, use_comm=True))
+    dbg("library-communicator training done")
     cbk = vq.ProductQuantizer(xs, m, k, iters, vq.Distance.euclidean(), engine=eng, init_idx=init, update=update,
                               reseed=lambda s: reseed_row, dist=RowShard.for_rank(n))
+    dbg("callback training done")
     assert np.array_equal(lib.codebooks.view(np.uint32), cbk.codebooks.view(np.uint32)), "library communicator != host callback"
     assert np.array_equal(lib.iters_run, cbk.iters_run)
     assert same_on_all_ranks(lib.codebooks), "replicated codebooks differ between ranks"
     single = vq.ProductQuantizer(torch.from_numpy(x).cuda(), m, k, iters, vq.Distance.euclidean(), engine=eng, init_idx=init,
                                  update=update, reseed=lambda s: reseed_row)
+    dbg("single-GPU training done")
     r1 = rel_diff(lib.codebooks, single.codebooks)
     assert r1 <= 1e-4, ("vs single GPU", r1)
     if rank == 0:
