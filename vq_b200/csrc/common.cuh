@@ -202,9 +202,10 @@ size_t vqb_tc_prep_bytes(size_t m);
 bool vqb_tc_supported(int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k, size_t sub_dim);
 int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t m, size_t k, void* prep,
                    const uint32_t* go = nullptr);
-// the 2-D tensor map over a row-major f32 matrix x[n, dim] used by the TMA-fed kernels: box = 32 floats x 128 rows, SWIZZLE_128B
+// the 2-D tensor map over a row-major f32 matrix x[n, dim] used by the TMA-fed kernels: box = box_cols floats x 128 rows
+// (32 columns: SWIZZLE_128B, one 128-byte line per row; otherwise unswizzled rows of box_cols floats)
 struct CUtensorMap_st;
-int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out);
+int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out, int box_cols = 32);
 int vqb_tc_assign_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k,
                          const void* prep, const int* active_dev, void* codes, uint32_t code_bytes,
                          size_t code_stride_row, size_t code_stride_sub, __half* recon,

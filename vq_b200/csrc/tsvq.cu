@@ -690,18 +690,16 @@ struct SlabView {
     void* p = nullptr;
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
+// The per-level tables live behind the call's fixed arrays in the context's grow-only workspace (no cudaMalloc per call
+// once the workspace has reached its size; the context mutex serialises its users).
 struct Slab {
-    DevBuf buf;
-    size_t off = 0;
-    cudaError_t ensure(size_t bytes) {  // callers synchronise the stream at the end of every level, so regrowing is safe
-        off = 0;
-        if (buf.bytes >= bytes) return cudaSuccess;
-        return buf.alloc(bytes + bytes / 2);
-    }
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
     static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
+    bool fits(size_t bytes) { off = 0; return bytes <= cap; }
     SlabView take(size_t bytes) {
         SlabView v;
-        v.p = static_cast<char*>(buf.p) + off;
+        v.p = base + off;
         off += pad(bytes);
         return v;
     }
@@ -804,14 +802,31 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     const bool warp_chains = vec_ok && dim % CS_SLICE == 0 && !old_colsum;  // else: block-wide ring kernel (any dim / alignment)
     const int n_slices = (int)(dim / CS_SLICE);
 
-    DevBuf perm_a, perm_b, vals;
-    VQB_CUDA(ctx, perm_a.alloc(n * 4));
-    VQB_CUDA(ctx, perm_b.alloc(n * 4));
-    VQB_CUDA(ctx, vals.alloc(n * 4));
-    k_iota<<<cdiv(n, 256), 256, 0, st>>>(perm_a.as<uint32_t>(), n);
+    // workspace: two row permutations, the split-coordinate values, then the per-level tables.  The widest level has at
+    // most min(2^max_depth, n) nodes; its tables are bounded by level_need() below.
+    const size_t max_level_nodes = (size_t)std::min<double>(std::ldexp(1.0, (int)std::min<size_t>(max_depth, 40)), (double)n);
+    auto level_need = [&](size_t ln, size_t cmax) {
+        return 3 * Slab::pad(ln * dim * 4) + 10 * Slab::pad(ln * 16) + Slab::pad(ln * 2 * 256 * 4) +
+               Slab::pad(ln * sizeof(SelState)) + 2 * Slab::pad((cmax + 1) * sizeof(Chunk)) + 4096;
+    };
+    const size_t fixed = 3 * Slab::pad(n * 4);
+    const size_t level_cap = level_need(max_level_nodes, n / PT_CHUNK + max_level_nodes + 1);
+    VQB_CUDA(ctx, vqb_ws_reserve(ctx, fixed + level_cap));
+    char* wsb = static_cast<char*>(ctx->ws);
+    uint32_t* perm = reinterpret_cast<uint32_t*>(wsb);
+    uint32_t* perm_next = reinterpret_cast<uint32_t*>(wsb + Slab::pad(n * 4));
+    SlabView vals;
+    vals.p = wsb + 2 * Slab::pad(n * 4);
+    k_iota<<<cdiv(n, 256), 256, 0, st>>>(perm, n);
     VQB_LAUNCHED(ctx);
-    uint32_t* perm = perm_a.as<uint32_t>();
-    uint32_t* perm_next = perm_b.as<uint32_t>();
+
+    // node centroids stay on the device: the levels come out in breadth-first id order, so every level's means are
+    // written straight behind the previous level's in the tree's own centroid table (bounded by 2^(depth+1)-1 and 2n-1
+    // nodes; a table that would not fit 1 GB is assembled through the host instead)
+    const double ub_nodes_d = std::min(std::ldexp(1.0, (int)std::min<size_t>(max_depth + 1, 41)) - 1.0, 2.0 * (double)n - 1.0);
+    const bool cent_on_device = ub_nodes_d * (double)dim * 4.0 <= 1024.0 * 1024.0 * 1024.0;
+    DevBuf tree_cent;
+    if (cent_on_device) VQB_CUDA(ctx, tree_cent.alloc((size_t)ub_nodes_d * dim * 4));
 
     std::vector<int32_t> h_left, h_right, h_split;
     std::vector<float> h_median;
@@ -823,6 +838,7 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     size_t n_nodes = 1;
 
     Slab slab;
+    slab.base = wsb + fixed; slab.cap = ctx->ws_bytes - fixed;
     while (!level.empty()) {
         const size_t ln = level.size();
         // ---- means of every node of the level (tsvq.rs:36) ----
@@ -831,11 +847,10 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         {   // everything this level can need: ln/sn-sized tables, three [nodes][dim] matrices, chunk tables
             size_t cmax = 0;
             for (size_t i = 0; i < ln; ++i) cmax += (level[i].len + PT_CHUNK - 1) / PT_CHUNK;
-            const size_t need = 3 * Slab::pad(ln * dim * 4) + 10 * Slab::pad(ln * 16) + Slab::pad(ln * 2 * 256 * 4) +
-                                Slab::pad(ln * sizeof(SelState)) + 2 * Slab::pad((cmax + 1) * sizeof(Chunk)) + 4096;
-            VQB_CUDA(ctx, slab.ensure(need));
+            if (!slab.fits(level_need(ln, cmax))) return vqb_fail(ctx, VQB_FAILURE, "internal: TSVQ level tables exceed the workspace");
         }
         SlabView d_segs = slab.take(ln * sizeof(NodeSeg)), d_mean = slab.take(ln * dim * 4);
+        if (cent_on_device) d_mean.p = tree_cent.as<float>() + (size_t)level[0].id * dim;   // this level's rows of the tree table
         VQB_CUDA(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), ln * sizeof(NodeSeg), cudaMemcpyHostToDevice, st));
         dim3 gcs(cdiv(dim, CS_SLICE), (unsigned)ln);
         if (gcs.y > 65535) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "too many nodes on one level");
@@ -849,8 +864,10 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         k_colsum<0><<<gcs, CS_THREADS, CS_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr,
                                                      d_mean.as<float>(), vec_ok);
         VQB_LAUNCHED(ctx);
-        level_cent.emplace_back(ln * dim);
-        VQB_CUDA(ctx, cudaMemcpyAsync(level_cent.back().data(), d_mean.p, ln * dim * 4, cudaMemcpyDeviceToHost, st));
+        if (!cent_on_device) {
+            level_cent.emplace_back(ln * dim);
+            VQB_CUDA(ctx, cudaMemcpyAsync(level_cent.back().data(), d_mean.p, ln * dim * 4, cudaMemcpyDeviceToHost, st));
+        }
 
         // ---- nodes that try to split (tsvq.rs:38) ----
         std::vector<uint32_t> split_idx;
@@ -964,19 +981,24 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     }
     VQB_CUDA(ctx, cudaStreamSynchronize(st));
 
-    // assemble the breadth-first centroid table (levels were produced in id order)
-    std::vector<float> cent(n_nodes * dim);
-    size_t off = 0;
-    for (auto& lc : level_cent) { std::memcpy(cent.data() + off, lc.data(), lc.size() * 4); off += lc.size(); }
-    if (off != n_nodes * dim) return vqb_fail(ctx, VQB_FAILURE, "internal: centroid table size mismatch");
+    // the breadth-first centroid table (levels were produced in id order)
+    std::vector<float> cent;
+    if (!cent_on_device) {
+        cent.resize(n_nodes * dim);
+        size_t off = 0;
+        for (auto& lc : level_cent) { std::memcpy(cent.data() + off, lc.data(), lc.size() * 4); off += lc.size(); }
+        if (off != n_nodes * dim) return vqb_fail(ctx, VQB_FAILURE, "internal: centroid table size mismatch");
+    }
 
     vqb_tsvq* t = new vqb_tsvq();
     t->ctx = ctx; t->dim = dim; t->n_nodes = n_nodes; t->metric = metric;
     t->h_left = h_left; t->h_right = h_right; t->h_split = h_split; t->h_median = h_median; t->h_count = h_count;
-    cudaError_t e = t->cent.alloc(n_nodes * dim * 4);
+    cudaError_t e = cudaSuccess;
+    if (cent_on_device) { std::swap(t->cent.p, tree_cent.p); std::swap(t->cent.bytes, tree_cent.bytes); }
+    else e = t->cent.alloc(n_nodes * dim * 4);
     if (e == cudaSuccess) e = t->left.alloc(n_nodes * 4);
     if (e == cudaSuccess) e = t->right.alloc(n_nodes * 4);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t->cent.p, cent.data(), n_nodes * dim * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !cent_on_device) e = cudaMemcpyAsync(t->cent.p, cent.data(), n_nodes * dim * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(t->left.p, h_left.data(), n_nodes * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(t->right.p, h_right.data(), n_nodes * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
