@@ -403,3 +403,27 @@ def test_api_shapes_and_errors(vq):
     r = ts.quantize_batch(data).astype(F)
     assert np.sqrt(np.mean((data - r) ** 2)) < 2.0
     assert ts.dim == 16 and "TSVQ" in repr(ts)
+
+
+@pytest.mark.parametrize("n,dim,m,k", [(5000, 64, 8, 256), (4097, 40, 5, 200), (9000, 96, 12, 17), (6000, 8, 1, 256)])
+def test_manhattan_tiled_kernel_equals_exact_and_oracle(vq, oracle, n, dim, m, k):
+    """sub_dim 8, k <= 256, n >= 4096: Manhattan encode runs the tiled kernel (k_assign_l1_tiles).  Codes and f16
+    reconstructions must equal the generic exact kernel and the oracle bit for bit, with a ragged last tile, a last column
+    group of fewer than four subspaces, NaN / Inf / zero rows and duplicate centroids (lowest index wins)."""
+    x = mixture(n, dim, 5)
+    d = dim // m
+    rng = np.random.default_rng(6)
+    cb = np.stack([x[rng.choice(n, k, replace=False), s * d:(s + 1) * d] for s in range(m)]).astype(F)
+    cb[0, min(3, k - 1)] = cb[0, 1]
+    x[0] = 0.0
+    x[1, :d] = np.nan
+    x[2, 0] = np.inf
+    x[n - 1] = -x[n - 2]
+    pq = vq.ProductQuantizer.from_codebooks(cb, vq.Distance.manhattan())
+    c_t, r_t = pq.encode_with_recon(x)                       # auto -> tiled kernel
+    c_e, r_e = pq.encode_with_recon(x, assign="exact")       # generic CUDA-core kernel
+    assert np.array_equal(c_t, c_e)
+    assert np.array_equal(bits(r_t), bits(r_e))
+    want_codes, want_recon = oracle.pq_encode(cb, "manhattan", x, sem="avx512")
+    assert np.array_equal(c_t.astype(np.uint32), want_codes)
+    assert np.array_equal(bits(r_t), bits(want_recon))

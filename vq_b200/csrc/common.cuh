@@ -196,6 +196,11 @@ int vqb_pq_assign_exact_launch(vqb_ctx* ctx, int metric_kind, const float* x, si
                                size_t code_stride_row, size_t code_stride_sub, __half* recon,
                                const int* n_sub_dev = nullptr, const uint32_t* go = nullptr);
 
+// tiled Manhattan assignment for sub_dim 8, k <= 256 (pq_assign.cu): coalesced row tiles, codebooks resident in smem
+bool vqb_l1_tiles_supported(int metric_kind, size_t sub_dim, size_t k);
+int vqb_assign_l1_tiles_launch(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, size_t k, const float* codebooks,
+                               void* codes, uint32_t code_bytes, size_t code_stride_row, size_t code_stride_sub, __half* recon);
+
 // tensor-core (tcgen05) GEMM-form assignment, pq_tc.cu.  `prep` is a device workspace of
 // vqb_tc_prep_bytes(m) bytes filled by vqb_tc_prepare from the current codebooks.
 size_t vqb_tc_prep_bytes(size_t m);

@@ -183,3 +183,153 @@ int vqb_pq_assign_exact_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, s
     }
     return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric kind %d", mk);
 }
+
+// =====================================================================================================================
+// Manhattan assignment for sub_dim 8, k <= 256 (BASELINE config 5b): tiled variant of the kernel above.
+//
+// Same arithmetic, operation for operation (n < 16: hsdlib's manhattan kernel is its scalar loop `sum += fabsf(a - b)`,
+// manhattan.c:132-163, the same sequential sum as the Rust fallback distance.rs:93-95), strict '<' / first minimum
+// (pq.rs:183-191).  What changes is the memory side:
+//   * a CTA owns 4 consecutive subspaces = one 128-byte line of every row and walks row tiles of 128 rows; the tile is
+//     staged with coalesced 16-byte loads (a warp reads four full lines per instruction) instead of 32-byte pieces at a
+//     3 KB stride (r01 profile: 15.2 GB of DRAM reads for 3.07 GB of input);
+//   * the four codebooks (32 KB) stay in shared memory for the CTA's life; a warp works on ONE subspace, so every centroid
+//     read is a broadcast; each thread carries two rows, so a centroid is read once per two distances;
+//   * codes leave through shared memory as one 4-byte store per row (encode layout) or 32-byte runs (training layout)
+//     instead of one-byte stores at a stride of m (3.05 GB written for 96 MB).
+namespace {
+
+constexpr int L1_D = 8, L1_G = 4, L1_ROWS = 128, L1_THREADS = 256;
+constexpr int L1_CB_BYTES = L1_G * 256 * L1_D * 4, L1_XT_BYTES = L1_ROWS * (L1_G * L1_D + 4) * 4;
+constexpr int L1_SMEM = L1_CB_BYTES + L1_XT_BYTES + L1_ROWS * 4;
+
+__global__ void __launch_bounds__(L1_THREADS)
+k_assign_l1_tiles(const float* __restrict__ x, size_t n, int dim, int m, int k, const float* __restrict__ codebooks,
+                  void* __restrict__ codes, uint32_t code_bytes, size_t stride_row, size_t stride_sub,
+                  __half* __restrict__ recon, int n_groups, int parts, int num_tiles) {
+    extern __shared__ __align__(16) uint8_t l1_smem[];
+    float (*cb)[256 * L1_D] = reinterpret_cast<float (*)[256 * L1_D]>(l1_smem);                       // [4][2048]: 32 KB
+    float (*xt)[L1_G * L1_D + 4] = reinterpret_cast<float (*)[L1_G * L1_D + 4]>(l1_smem + L1_CB_BYTES); // rows padded to 144 B: conflict-free 16-byte reads
+    uint32_t* ct = reinterpret_cast<uint32_t*>(l1_smem + L1_CB_BYTES + L1_XT_BYTES);                    // 4 codes (bytes) per row
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = blockIdx.x % n_groups, part = blockIdx.x / n_groups;
+    const int s0 = grp * L1_G;
+    const int g_cnt = min(L1_G, m - s0);
+    for (int i = 0; i < g_cnt; ++i)
+        for (int t = tid; t < k * L1_D / 4; t += L1_THREADS)
+            reinterpret_cast<float4*>(cb[i])[t] = __ldg(reinterpret_cast<const float4*>(codebooks + (size_t)(s0 + i) * k * L1_D) + t);
+    const int si = warp & 3;              // subspace of this warp
+    const int rbase = (warp >> 2) * 64;   // its 64 rows: lane -> rows rbase + lane, rbase + 32 + lane
+    const bool sub_ok = si < g_cnt;
+    const bool vec_ok = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (s0 * L1_D + L1_G * L1_D <= dim);
+    for (int it = part; it < num_tiles; it += parts) {
+        const size_t row0 = (size_t)it * L1_ROWS;
+        __syncthreads();   // previous tile's readers are done (and the codebooks are staged)
+        // ---- stage the tile: 128 rows x 8 float4; consecutive threads take consecutive 16-byte pieces of a row
+        for (int t = tid; t < L1_ROWS * 8; t += L1_THREADS) {
+            const int r = t >> 3, c4 = t & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n) {
+                const float* src = x + (row0 + r) * (size_t)dim + (size_t)s0 * L1_D + c4 * 4;
+                if (vec_ok) v = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    const int col = s0 * L1_D + c4 * 4;
+                    v.x = col < dim ? __ldg(src) : 0.f; v.y = col + 1 < dim ? __ldg(src + 1) : 0.f;
+                    v.z = col + 2 < dim ? __ldg(src + 2) : 0.f; v.w = col + 3 < dim ? __ldg(src + 3) : 0.f;
+                }
+            }
+            *reinterpret_cast<float4*>(&xt[r][c4 * 4]) = v;
+        }
+        if (tid < L1_ROWS) ct[tid] = 0;
+        __syncthreads();
+        if (sub_ok) {
+            float xa[L1_D], xb[L1_D];
+            {
+                const float4 a0 = *reinterpret_cast<const float4*>(&xt[rbase + lane][si * 8]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&xt[rbase + lane][si * 8 + 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&xt[rbase + 32 + lane][si * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&xt[rbase + 32 + lane][si * 8 + 4]);
+                xa[0] = a0.x; xa[1] = a0.y; xa[2] = a0.z; xa[3] = a0.w; xa[4] = a1.x; xa[5] = a1.y; xa[6] = a1.z; xa[7] = a1.w;
+                xb[0] = b0.x; xb[1] = b0.y; xb[2] = b0.z; xb[3] = b0.w; xb[4] = b1.x; xb[5] = b1.y; xb[6] = b1.z; xb[7] = b1.w;
+            }
+            const float* c = cb[si];
+            // index 0 seeds the minimum whatever its value (a NaN there is never replaced), then strict '<'
+            float best_a, best_b;
+            uint32_t ja = 0, jb = 0;
+            {
+                float da = 0.f, db = 0.f;
+#pragma unroll
+                for (int i = 0; i < L1_D; ++i) {
+                    da = __fadd_rn(da, fabsf(__fsub_rn(xa[i], c[i])));
+                    db = __fadd_rn(db, fabsf(__fsub_rn(xb[i], c[i])));
+                }
+                best_a = da; best_b = db;
+            }
+#pragma unroll 4
+            for (int j = 1; j < k; ++j) {
+                const float4 c0 = *reinterpret_cast<const float4*>(c + j * L1_D);
+                const float4 c1 = *reinterpret_cast<const float4*>(c + j * L1_D + 4);
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                float da = 0.f, db = 0.f;
+#pragma unroll
+                for (int i = 0; i < L1_D; ++i) {
+                    da = __fadd_rn(da, fabsf(__fsub_rn(xa[i], cc[i])));
+                    db = __fadd_rn(db, fabsf(__fsub_rn(xb[i], cc[i])));
+                }
+                if (da < best_a) { best_a = da; ja = (uint32_t)j; }
+                if (db < best_b) { best_b = db; jb = (uint32_t)j; }
+            }
+            // ---- codes: through shared memory for the row-major layout, direct 32-byte runs for the subspace-major one
+            const size_t ra = row0 + rbase + lane, rb = ra + 32;
+            const size_t s = (size_t)(s0 + si);
+            if (code_bytes == 1 && stride_sub == 1 && codes) {
+                atomicOr(&ct[rbase + lane], ja << (8 * si));
+                atomicOr(&ct[rbase + 32 + lane], jb << (8 * si));
+            } else if (codes) {
+                if (ra < n) store_code_any(codes, code_bytes, ra * stride_row + s * stride_sub, ja);
+                if (rb < n) store_code_any(codes, code_bytes, rb * stride_row + s * stride_sub, jb);
+            }
+            if (recon) {  // pq.rs:193-195: f16::from_f32 of the chosen centroid
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const size_t rr = h ? rb : ra;
+                    if (rr >= n) continue;
+                    const float* cp = c + (h ? jb : ja) * L1_D;
+                    __half2 hh[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) hh[q] = __floats2half2_rn(cp[2 * q], cp[2 * q + 1]);
+                    __half* dst = recon + rr * (size_t)dim + s * L1_D;
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(hh);
+                    else for (int q = 0; q < 4; ++q) { dst[2 * q] = __low2half(hh[q]); dst[2 * q + 1] = __high2half(hh[q]); }
+                }
+            }
+        }
+        if (code_bytes == 1 && stride_sub == 1 && codes) {
+            __syncthreads();
+            if (tid < L1_ROWS && row0 + tid < n) {
+                uint8_t* dst = static_cast<uint8_t*>(codes) + (row0 + tid) * stride_row + s0;
+                const uint32_t w = ct[tid];
+                if (g_cnt == 4 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = w;
+                else for (int i = 0; i < g_cnt; ++i) dst[i] = (uint8_t)(w >> (8 * i));
+            }
+        }
+    }
+}
+
+}  // namespace
+
+bool vqb_l1_tiles_supported(int mk, size_t d, size_t k) { return mk == MK_MANHATTAN && d == L1_D && k >= 1 && k <= 256; }
+
+int vqb_assign_l1_tiles_launch(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, size_t k, const float* cb,
+                               void* codes, uint32_t code_bytes, size_t stride_row, size_t stride_sub, __half* recon) {
+    if (n == 0) return VQB_SUCCESS;
+    const int n_groups = (int)((m + L1_G - 1) / L1_G);
+    const int num_tiles = (int)cdiv(n, L1_ROWS);
+    // 4 CTAs of 256 threads per SM (~52 KB of shared memory, 47 registers each): the kernel is FP32-issue bound
+    const int parts = std::max(1, std::min(num_tiles, 4 * ctx->sm_count / n_groups));
+    VQB_CUDA(ctx, cudaFuncSetAttribute(k_assign_l1_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, L1_SMEM));
+    k_assign_l1_tiles<<<n_groups * parts, L1_THREADS, L1_SMEM, ctx->stream>>>(x, n, (int)dim, (int)m, (int)k, cb, codes, code_bytes,
+                                                                        stride_row, stride_sub, recon, n_groups, parts, num_tiles);
+    VQB_LAUNCHED(ctx);
+    return VQB_SUCCESS;
+}

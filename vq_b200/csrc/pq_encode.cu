@@ -83,6 +83,9 @@ int encode_device(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, vo
     if (use_tc)
         rc = vqb_tc_assign_launch(ctx, pq->metric, x, n, dim, pq->m, pq->k, pq->tc_prep.p, nullptr, codes, code_bytes,
                                   /*stride_row=*/pq->m, /*stride_sub=*/1, recon);
+    else if (vqb_l1_tiles_supported(pq->metric, pq->d, pq->k) && n >= 4096 && assign_mode != VQB_ASSIGN_EXACT)
+        rc = vqb_assign_l1_tiles_launch(ctx, x, n, dim, pq->m, pq->k, pq->cb.as<float>(), codes, code_bytes,
+                                        /*stride_row=*/pq->m, /*stride_sub=*/1, recon);
     else
         rc = vqb_pq_assign_exact_launch(ctx, pq->metric, x, n, pq->m * pq->d, pq->m, pq->k, pq->d,
                                         pq->cb.as<float>(), nullptr, (int)pq->m, codes, code_bytes,
