@@ -236,8 +236,15 @@ def measure_paths(eng, ext, x, pq, peaks):
         h = C.c_void_p()
         eng.check(lib.vqb_tsvq_train(eng.h, x4.data_ptr(), n4, d2, 8, 1, C.byref(h)))
         hs.append(h)
-    t = timed(build, reps=2, warm=1)
+    build(); build()                               # warm: workspace slab at size, kernels resident
+    tb = []
+    for _ in range(7):                             # the build synchronises once per level: time every call on the host clock
+        torch.cuda.synchronize(); t0 = time.perf_counter(); build(); torch.cuda.synchronize()
+        tb.append(time.perf_counter() - t0)
+    t = statistics.median(tb)
     hbm_entry("tsvq_build_depth8_1Mx1536", t, (2 * 8 + 1) * n4 * d2 * 4, n4, "Mvec/s")
+    res["tsvq_build_depth8_1Mx1536"]["ms_min"] = min(tb) * 1e3
+    res["tsvq_build_depth8_1Mx1536"]["ms_max"] = max(tb) * 1e3
     tree = hs[-1]
     for h in hs[:-1]:
         lib.vqb_tsvq_destroy(h)
@@ -311,6 +318,39 @@ def measure_paths(eng, ext, x, pq, peaks):
     rec = torch.empty(rows, dim, device="cuda")
     t = timed(lambda: eng.check(lib.vqb_pq_decode(pq._handle, codes.data_ptr(), 1, rows, rec.data_ptr())))
     hbm_entry("pq_decode", t, rows * (M + dim * 4), rows, "Mvec/s")
+    del rec
+
+    # ---- the same entry points with HOST buffers (pinned): chunked three-stream pipeline, PCIe inside the timing ----
+    def wall(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+    try:
+        nh, dh = 400_000, 1536
+        hx = eng.pinned_empty((nh, dh), np.float32); hq = eng.pinned_empty((nh, dh), np.uint8)
+        hx[:] = np.random.default_rng(5).standard_normal((nh, dh), dtype=np.float32) * np.float32(0.5)
+        neh = nh * dh
+        e2e = {}
+        t = wall(lambda: eng.check(lib.vqb_bq_quantize(eng.h, hx.ctypes.data, neh, 0.0, 0, 1, hq.ctypes.data)))
+        e2e["bq_quantize_1536d"] = {"Mvec/s": nh / t / 1e6, "GB/s_in": neh * 4 / t / 1e9}
+        t = wall(lambda: eng.check(lib.vqb_sq_quantize(eng.h, hx.ctypes.data, neh, -1.0, 1.0, float(step), 256, hq.ctypes.data)))
+        e2e["sq8_quantize_1536d"] = {"Mvec/s": nh / t / 1e6, "GB/s_in": neh * 4 / t / 1e9}
+        t = wall(lambda: eng.check(lib.vqb_sq_dequantize(eng.h, hq.ctypes.data, neh, -1.0, float(step), hx.ctypes.data)))
+        e2e["sq8_dequantize_1536d"] = {"Mvec/s": nh / t / 1e6, "GB/s_out": neh * 4 / t / 1e9}
+        hc = eng.pinned_empty((nh, M), np.uint8); hc[:] = codes[:nh].cpu().numpy()
+        hr = eng.pinned_empty((nh, dim), np.float32)
+        t = wall(lambda: eng.check(lib.vqb_pq_decode(pq._handle, hc.ctypes.data, 1, nh, hr.ctypes.data)))
+        e2e["pq_decode"] = {"Mvec/s": nh / t / 1e6, "GB/s_out": nh * dim * 4 / t / 1e9}
+        # single-vector quantize, the reference's own call shape (src/pq.rs:167; loop at src/bin/eval_pq.rs:53-58)
+        v1 = np.ascontiguousarray(x[:1].cpu().numpy()); o1 = np.empty(dim, np.float16)
+        t = wall(lambda: eng.check(lib.vqb_pq_encode(pq._handle, v1.ctypes.data, 1, 0, None, 1, o1.ctypes.data)), reps=200)
+        e2e["pq_quantize_single_vector"] = {"us_per_call": t * 1e6, "note": "host f32[768] in, f16[768] out, exact CUDA-core kernel (n < 1024)"}
+        res["host_buffers"] = e2e
+    except Exception as ex:
+        res["host_buffers"] = {"error": repr(ex)[:200]}
     return res
 
 

@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -154,13 +156,17 @@ struct InputView {
     DevBuf staging;
     const void* dev = nullptr;
     bool was_host = false;
-    int bind(vqb_ctx* ctx, const void* p, size_t bytes) {
+    // slot >= 0: the device copy lives in the context's grow-only staging slot `slot` (no cudaMalloc / cudaFree per call;
+    // the caller holds ctx->mu and synchronises before returning); slot < 0: a buffer owned by this view
+    int bind(vqb_ctx* ctx, const void* p, size_t bytes, int slot = -1) {
         if (bytes == 0) { dev = p; return VQB_SUCCESS; }
         if (vqb_is_device_ptr(p)) { dev = p; return VQB_SUCCESS; }
         was_host = true;
-        VQB_CUDA(ctx, staging.alloc(bytes));
-        VQB_CUDA(ctx, cudaMemcpyAsync(staging.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        dev = staging.p;
+        void* d = nullptr;
+        if (slot >= 0) VQB_CUDA(ctx, vqb_stage(ctx, slot, bytes, &d));
+        else { VQB_CUDA(ctx, staging.alloc(bytes)); d = staging.p; }
+        VQB_CUDA(ctx, cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        dev = d;
         return VQB_SUCCESS;
     }
 };
@@ -186,6 +192,80 @@ struct OutputView {
         return VQB_SUCCESS;
     }
 };
+
+// ---- chunked three-stream pipeline for calls whose buffers live on the HOST ------------------------------------------
+// Units [0, n) (rows or elements) are processed in chunks: H2D on ctx->copy_in | kernels on ctx->stream | D2H on
+// ctx->copy_out, double-buffered through the context's grow-only staging slots (0/1 input, 2/3 first output, 4/5 second
+// output), so the PCIe copies of chunk c+1 and c-1 overlap the kernels of chunk c and no call allocates after the first.
+// Any of the three buffers may also be a device pointer (then it is used in place).  Whatever happens -- including an
+// error return half-way -- all three streams are drained before the call returns, so no copy is left writing into the
+// caller's buffers or the staging slots.
+struct ChunkIo {
+    const void* in = nullptr;  size_t in_unit = 0;     // bytes per unit
+    void* out0 = nullptr;      size_t out0_unit = 0;   // may be null
+    void* out1 = nullptr;      size_t out1_unit = 0;   // may be null
+};
+inline size_t vqb_chunk_bytes() {
+    static const size_t mb = [] { const char* e = std::getenv("VQB_CHUNK_MB"); long v = e ? std::atol(e) : 0; return (size_t)(v > 0 ? v : 64); }();
+    return mb << 20;
+}
+template <typename Launch>   // int launch(const void* in_dev, void* out0_dev, void* out1_dev, size_t units, size_t unit0)
+int vqb_chunk_pipeline(vqb_ctx* ctx, size_t n, const ChunkIo& io, Launch&& launch) {
+    if (n == 0) return VQB_SUCCESS;
+    const bool in_dev = vqb_is_device_ptr(io.in);
+    const bool o0_dev = !io.out0 || vqb_is_device_ptr(io.out0);
+    const bool o1_dev = !io.out1 || vqb_is_device_ptr(io.out1);
+    if (in_dev && o0_dev && o1_dev) return launch(io.in, io.out0, io.out1, n, 0);   // all on the device: one asynchronous enqueue
+    // chunk = 64 MB of the widest of the three streams of bytes (decode grows 32-fold on the way out)
+    const size_t widest = std::max(std::max(io.in_unit, io.out0 ? io.out0_unit : 0), std::max<size_t>(io.out1 ? io.out1_unit : 0, 1));
+    size_t chunk = std::max<size_t>(1, vqb_chunk_bytes() / widest);
+    chunk = std::min(chunk, n);
+    for (int i = 0; i < 7; ++i)
+        if (!ctx->stage_ev[i]) VQB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    void *sin[2] = {nullptr, nullptr}, *so0[2] = {nullptr, nullptr}, *so1[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; ++b) {
+        if (!in_dev) VQB_CUDA(ctx, vqb_stage(ctx, b, chunk * io.in_unit, &sin[b]));
+        if (io.out0 && !o0_dev) VQB_CUDA(ctx, vqb_stage(ctx, 2 + b, chunk * io.out0_unit, &so0[b]));
+        if (io.out1 && !o1_dev) VQB_CUDA(ctx, vqb_stage(ctx, 4 + b, chunk * io.out1_unit, &so1[b]));
+    }
+    cudaEvent_t* ev_in = &ctx->stage_ev[0];     // [2] chunk uploaded
+    cudaEvent_t* ev_comp = &ctx->stage_ev[2];   // [2] chunk computed
+    cudaEvent_t* ev_out = &ctx->stage_ev[4];    // [2] chunk downloaded
+    struct Drain {   // no copy or kernel of this call outlives it, on any return path
+        vqb_ctx* c;
+        ~Drain() { cudaStreamSynchronize(c->copy_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_out); }
+    } drain{ctx};
+    // order the pipeline after whatever is already queued on the context stream
+    VQB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[6], ctx->stream));
+    VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->stage_ev[6], 0));
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c & 1);
+        const size_t u0 = c * chunk, units = std::min(chunk, n - u0);
+        const void* din = static_cast<const char*>(io.in) + u0 * io.in_unit;
+        if (!in_dev) {
+            if (c >= 2) VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_comp[b], 0));   // staging b consumed
+            VQB_CUDA(ctx, cudaMemcpyAsync(sin[b], din, units * io.in_unit, cudaMemcpyHostToDevice, ctx->copy_in));
+            VQB_CUDA(ctx, cudaEventRecord(ev_in[b], ctx->copy_in));
+            VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[b], 0));
+            din = sin[b];
+        }
+        if (c >= 2) VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[b], 0));           // output staging b drained
+        void* d0 = io.out0 ? (o0_dev ? static_cast<char*>(io.out0) + u0 * io.out0_unit : so0[b]) : nullptr;
+        void* d1 = io.out1 ? (o1_dev ? static_cast<char*>(io.out1) + u0 * io.out1_unit : so1[b]) : nullptr;
+        VQB_TRY(launch(din, d0, d1, units, u0));
+        VQB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
+        VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_comp[b], 0));
+        if (io.out0 && !o0_dev)
+            VQB_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(io.out0) + u0 * io.out0_unit, so0[b], units * io.out0_unit,
+                                          cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (io.out1 && !o1_dev)
+            VQB_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(io.out1) + u0 * io.out1_unit, so1[b], units * io.out1_unit,
+                                          cudaMemcpyDeviceToHost, ctx->copy_out));
+        VQB_CUDA(ctx, cudaEventRecord(ev_out[b], ctx->copy_out));
+    }
+    return VQB_SUCCESS;   // ~Drain synchronises the three streams
+}
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -161,19 +161,19 @@ int run_f32_to_u8(vqb_ctx* ctx, const float* x, size_t n, uint8_t* out, Op op) {
     if (n == 0) return VQB_SUCCESS;  // empty input is legal (tests/integration_tests.rs:296-310)
     if (!x || !out) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null data pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    InputView in; OutputView ov;
-    VQB_TRY(in.bind(ctx, x, n * sizeof(float)));
-    VQB_TRY(ov.bind(ctx, out, n));
-    const float* dx = static_cast<const float*>(in.dev);
-    uint8_t* dout = static_cast<uint8_t*>(ov.dev);
-    if (aligned_to(dx, 16) && aligned_to(dout, 4))
-        k_f32_to_u8<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->stream>>>(dx, dout, n, op);
-    else
-        k_f32_to_u8_unaligned<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->stream>>>(dx, dout, n, op);
-    VQB_LAUNCHED(ctx);
-    VQB_TRY(ov.finish(ctx));
-    if (in.was_host || ov.host) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VQB_SUCCESS;
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ChunkIo io; io.in = x; io.in_unit = 4; io.out0 = out; io.out0_unit = 1;
+    // host buffers: 64 MB chunks, copies overlapped with the kernels (BASELINE config 2 does not fit any other way)
+    return vqb_chunk_pipeline(ctx, n, io, [&](const void* din, void* d0, void*, size_t units, size_t) -> int {
+        const float* dx = static_cast<const float*>(din);
+        uint8_t* dout = static_cast<uint8_t*>(d0);
+        if (aligned_to(dx, 16) && aligned_to(dout, 4))
+            k_f32_to_u8<<<ew_grid(ctx, units), EW_THREADS, 0, ctx->stream>>>(dx, dout, units, op);
+        else
+            k_f32_to_u8_unaligned<<<ew_grid(ctx, units), EW_THREADS, 0, ctx->stream>>>(dx, dout, units, op);
+        VQB_LAUNCHED(ctx);
+        return VQB_SUCCESS;
+    });
 }
 
 template <typename Op>
@@ -182,19 +182,18 @@ int run_u8_to_f32(vqb_ctx* ctx, const uint8_t* c, size_t n, float* out, Op op) {
     if (n == 0) return VQB_SUCCESS;
     if (!c || !out) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null data pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    InputView in; OutputView ov;
-    VQB_TRY(in.bind(ctx, c, n));
-    VQB_TRY(ov.bind(ctx, out, n * sizeof(float)));
-    const uint8_t* dc = static_cast<const uint8_t*>(in.dev);
-    float* dout = static_cast<float*>(ov.dev);
-    if (aligned_to(dc, 4) && aligned_to(dout, 16))
-        k_u8_to_f32<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->stream>>>(dc, dout, n, op);
-    else
-        k_u8_to_f32_unaligned<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->stream>>>(dc, dout, n, op);
-    VQB_LAUNCHED(ctx);
-    VQB_TRY(ov.finish(ctx));
-    if (in.was_host || ov.host) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VQB_SUCCESS;
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ChunkIo io; io.in = c; io.in_unit = 1; io.out0 = out; io.out0_unit = 4;
+    return vqb_chunk_pipeline(ctx, n, io, [&](const void* din, void* d0, void*, size_t units, size_t) -> int {
+        const uint8_t* dc = static_cast<const uint8_t*>(din);
+        float* dout = static_cast<float*>(d0);
+        if (aligned_to(dc, 4) && aligned_to(dout, 16))
+            k_u8_to_f32<<<ew_grid(ctx, units), EW_THREADS, 0, ctx->stream>>>(dc, dout, units, op);
+        else
+            k_u8_to_f32_unaligned<<<ew_grid(ctx, units), EW_THREADS, 0, ctx->stream>>>(dc, dout, units, op);
+        VQB_LAUNCHED(ctx);
+        return VQB_SUCCESS;
+    });
 }
 
 }  // namespace
@@ -228,16 +227,14 @@ int vqb_f16_dequantize(vqb_ctx* ctx, const uint16_t* q, size_t n, float* out) {
     if (n == 0) return VQB_SUCCESS;
     if (!q || !out) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null data pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    InputView in; OutputView ov;
-    VQB_TRY(in.bind(ctx, q, n * 2));
-    VQB_TRY(ov.bind(ctx, out, n * sizeof(float)));
-    int al = aligned_to(in.dev, 8) && aligned_to(ov.dev, 16);
-    k_f16_to_f32<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->stream>>>(static_cast<const __half*>(in.dev),
-                                                                  static_cast<float*>(ov.dev), n, al);
-    VQB_LAUNCHED(ctx);
-    VQB_TRY(ov.finish(ctx));
-    if (in.was_host || ov.host) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VQB_SUCCESS;
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ChunkIo io; io.in = q; io.in_unit = 2; io.out0 = out; io.out0_unit = 4;
+    return vqb_chunk_pipeline(ctx, n, io, [&](const void* din, void* d0, void*, size_t units, size_t) -> int {
+        int al = aligned_to(din, 8) && aligned_to(d0, 16);
+        k_f16_to_f32<<<ew_grid(ctx, units), EW_THREADS, 0, ctx->stream>>>(static_cast<const __half*>(din), static_cast<float*>(d0), units, al);
+        VQB_LAUNCHED(ctx);
+        return VQB_SUCCESS;
+    });
 }
 
 int vqb_distance_batch(vqb_ctx* ctx, int metric, const float* a, const float* b, size_t rows, size_t n,

@@ -161,57 +161,15 @@ int vqb_pq_encode(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, vo
     const bool x_dev = vqb_is_device_ptr(x);
     const bool c_dev = !codes_out || vqb_is_device_ptr(codes_out);
     const bool r_dev = !recon_out || vqb_is_device_ptr(recon_out);
-    if (x_dev && c_dev && r_dev)  // all on device: one asynchronous launch
-        return encode_device(pq, x, n, assign_mode, codes_out, code_bytes, reinterpret_cast<__half*>(recon_out));
-
-    // ---- chunked three-stream pipeline (staging buffers and events live in the context) ----
-    static const size_t chunk_mb = [] { const char* e = std::getenv("VQB_CHUNK_MB"); long v = e ? std::atol(e) : 0; return (size_t)(v > 0 ? v : 64); }();
-    size_t chunk_rows = std::max<size_t>(1, (chunk_mb << 20) / (dim * sizeof(float)));
-    chunk_rows = std::min(chunk_rows, n);
-    Buf xin[2], cst[2], rst[2];
-    Ev ev_in[2], ev_comp[2], ev_out[2], ev_start;
-    for (int i = 0; i < 7; ++i)
-        if (!ctx->stage_ev[i]) VQB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
-    for (int b = 0; b < 2; ++b) {
-        if (!x_dev) VQB_CUDA(ctx, vqb_stage(ctx, b, chunk_rows * dim * 4, &xin[b].p));
-        if (codes_out && !c_dev) VQB_CUDA(ctx, vqb_stage(ctx, 2 + b, chunk_rows * pq->m * code_bytes, &cst[b].p));
-        if (recon_out && !r_dev) VQB_CUDA(ctx, vqb_stage(ctx, 4 + b, chunk_rows * dim * 2, &rst[b].p));
-        ev_in[b].e = ctx->stage_ev[b]; ev_comp[b].e = ctx->stage_ev[2 + b]; ev_out[b].e = ctx->stage_ev[4 + b];
-    }
-    // order the pipeline after whatever is already queued on the context stream
-    ev_start.e = ctx->stage_ev[6];
-    VQB_CUDA(ctx, cudaEventRecord(ev_start.e, ctx->stream));
-    VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_start.e, 0));
-    size_t n_chunks = (n + chunk_rows - 1) / chunk_rows;
-    for (size_t c = 0; c < n_chunks; ++c) {
-        int b = (int)(c & 1);
-        size_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
-        const float* xd = x + r0 * dim;
-        if (!x_dev) {
-            if (c >= 2) VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_comp[b].e, 0));  // buffer b consumed
-            VQB_CUDA(ctx, cudaMemcpyAsync(xin[b].p, x + r0 * dim, rows * dim * 4, cudaMemcpyHostToDevice, ctx->copy_in));
-            VQB_CUDA(ctx, cudaEventRecord(ev_in[b].e, ctx->copy_in));
-            VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[b].e, 0));
-            xd = xin[b].as<float>();
-        }
-        if (c >= 2) VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[b].e, 0));  // staging b drained
-        void* cd = codes_out ? (c_dev ? (void*)((char*)codes_out + r0 * pq->m * code_bytes) : cst[b].p) : nullptr;
-        __half* rd = recon_out ? (r_dev ? reinterpret_cast<__half*>(recon_out) + r0 * dim : rst[b].as<__half>()) : nullptr;
-        VQB_TRY(encode_device(pq, xd, rows, assign_mode, cd, code_bytes, rd));
-        VQB_CUDA(ctx, cudaEventRecord(ev_comp[b].e, ctx->stream));
-        VQB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_comp[b].e, 0));
-        if (codes_out && !c_dev)
-            VQB_CUDA(ctx, cudaMemcpyAsync((char*)codes_out + r0 * pq->m * code_bytes, cst[b].p,
-                                          rows * pq->m * code_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
-        if (recon_out && !r_dev)
-            VQB_CUDA(ctx, cudaMemcpyAsync(recon_out + r0 * dim, rst[b].p, rows * dim * 2, cudaMemcpyDeviceToHost,
-                                          ctx->copy_out));
-        VQB_CUDA(ctx, cudaEventRecord(ev_out[b].e, ctx->copy_out));
-    }
-    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_in));
-    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    VQB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
-    return VQB_SUCCESS;
+    (void)x_dev; (void)c_dev; (void)r_dev;
+    // host buffers: row chunks over three streams (common.cuh); device buffers: one asynchronous launch
+    ChunkIo io;
+    io.in = x; io.in_unit = dim * sizeof(float);
+    io.out0 = codes_out; io.out0_unit = pq->m * code_bytes;
+    io.out1 = recon_out; io.out1_unit = dim * sizeof(uint16_t);
+    return vqb_chunk_pipeline(ctx, n, io, [&](const void* din, void* d0, void* d1, size_t rows, size_t) -> int {
+        return encode_device(pq, static_cast<const float*>(din), rows, assign_mode, d0, code_bytes, static_cast<__half*>(d1));
+    });
 }
 
 int vqb_pq_decode(vqb_pq* pq, const void* codes, uint32_t code_bytes, size_t n, float* out) {
@@ -222,25 +180,25 @@ int vqb_pq_decode(vqb_pq* pq, const void* codes, uint32_t code_bytes, size_t n, 
     if (code_bytes != 1 && code_bytes != 2 && code_bytes != 4)
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "code_bytes must be 1, 2 or 4");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    VQB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t dim = pq->m * pq->d;
-    InputView in; OutputView ov;
-    VQB_TRY(in.bind(ctx, codes, n * pq->m * code_bytes));
-    VQB_TRY(ov.bind(ctx, out, n * dim * 4));
-    if (pq->d % 4 == 0 && (reinterpret_cast<uintptr_t>(ov.dev) & 15) == 0) {
-        const unsigned grid = (unsigned)std::min<size_t>(cdiv(n * pq->m * (pq->d / 4), 256), (size_t)ctx->sm_count * 64);
-        float* o = static_cast<float*>(ov.dev);
-        if (code_bytes == 1) k_pq_decode_v4<1><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
-        else if (code_bytes == 2) k_pq_decode_v4<2><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
-        else k_pq_decode_v4<4><<<grid, 256, 0, ctx->stream>>>(in.dev, n, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
-    } else {
-        k_pq_decode<<<cdiv(n * dim, 256), 256, 0, ctx->stream>>>(in.dev, code_bytes, n, (int)pq->m, (int)pq->k,
-                                                                (int)pq->d, pq->cb.as<float>(),
-                                                                static_cast<float*>(ov.dev));
-    }
-    VQB_LAUNCHED(ctx);
-    VQB_TRY(ov.finish(ctx));
-    if (in.was_host || ov.host) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VQB_SUCCESS;
+    ChunkIo io;
+    io.in = codes; io.in_unit = pq->m * code_bytes;
+    io.out0 = out; io.out0_unit = dim * sizeof(float);
+    return vqb_chunk_pipeline(ctx, n, io, [&](const void* din, void* d0, void*, size_t rows, size_t) -> int {
+        float* o = static_cast<float*>(d0);
+        if (pq->d % 4 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            const unsigned grid = (unsigned)std::min<size_t>(cdiv(rows * pq->m * (pq->d / 4), 256), (size_t)ctx->sm_count * 64);
+            if (code_bytes == 1) k_pq_decode_v4<1><<<grid, 256, 0, ctx->stream>>>(din, rows, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
+            else if (code_bytes == 2) k_pq_decode_v4<2><<<grid, 256, 0, ctx->stream>>>(din, rows, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
+            else k_pq_decode_v4<4><<<grid, 256, 0, ctx->stream>>>(din, rows, (int)pq->m, (int)pq->k, (int)pq->d, pq->cb.as<float>(), o);
+        } else {
+            k_pq_decode<<<cdiv(rows * dim, 256), 256, 0, ctx->stream>>>(din, code_bytes, rows, (int)pq->m, (int)pq->k, (int)pq->d,
+                                                                       pq->cb.as<float>(), o);
+        }
+        VQB_LAUNCHED(ctx);
+        return VQB_SUCCESS;
+    });
 }
 
 }  // extern "C"

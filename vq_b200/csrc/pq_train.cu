@@ -961,7 +961,7 @@ int vqb_pq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, s
 
     const double t_enter = trace_on() ? now_ms() : 0.0;
     InputView xin;
-    VQB_TRY(xin.bind(ctx, x, n * dim * sizeof(float)));
+    VQB_TRY(xin.bind(ctx, x, n * dim * sizeof(float), /*slot=*/0));
     TrainWs ws;
     VQB_TRY(ws.setup(ctx, static_cast<const float*>(xin.dev), n, dim, m, k, o.update_mode));
     if (trace_on()) std::fprintf(stderr, "[vqb trace] bind + workspace: %.3f ms (update kind %d)\n", now_ms() - t_enter, ws.kind);
@@ -1081,7 +1081,7 @@ int vqb_pq_assign_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size
     VQB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t d = dim / m;
     InputView xin; OutputView ov;
-    VQB_TRY(xin.bind(ctx, x, n * dim * 4));
+    VQB_TRY(xin.bind(ctx, x, n * dim * 4, /*slot=*/0));
     VQB_TRY(ov.bind(ctx, codes_out, m * n * 4));
     TrainWs ws;
     VQB_TRY(ws.setup(ctx, static_cast<const float*>(xin.dev), n, dim, m, k, VQB_UPDATE_ORDERED, /*assign_only=*/true));
@@ -1109,7 +1109,7 @@ int vqb_pq_train_step(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t
     if (use_comm && !ctx->nccl_comm)
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "VQB_TRAIN_USE_COMM needs vqb_comm_init_rank on this context first");
     InputView xin;
-    VQB_TRY(xin.bind(ctx, x, n * dim * 4));
+    VQB_TRY(xin.bind(ctx, x, n * dim * 4, /*slot=*/0));
     TrainWs ws;
     VQB_TRY(ws.setup(ctx, static_cast<const float*>(xin.dev), n, dim, m, k, o.update_mode));
     VQB_CUDA(ctx, cudaMemcpyAsync(ws.cb, codebooks_inout, m * k * d * 4, cudaMemcpyDefault, ctx->stream));

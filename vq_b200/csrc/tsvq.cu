@@ -788,7 +788,7 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     cudaStream_t st = ctx->stream;
 
     InputView xin;
-    VQB_TRY(xin.bind(ctx, x, n * dim * 4));
+    VQB_TRY(xin.bind(ctx, x, n * dim * 4, /*slot=*/0));
     const float* xd = static_cast<const float*>(xin.dev);
     const int vec_ok = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(xd) & 15) == 0);
     VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
@@ -1016,19 +1016,16 @@ int vqb_tsvq_encode(vqb_tsvq* t, const float* x, size_t n, uint32_t* leaf_out, u
     std::lock_guard<std::mutex> lk(ctx->mu);
     VQB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t dim = t->dim;
-    // host inputs/outputs are processed in row chunks so arbitrarily large batches fit
-    const bool all_dev = vqb_is_device_ptr(x) && (!leaf_out || vqb_is_device_ptr(leaf_out)) &&
-                         (!recon_out || vqb_is_device_ptr(recon_out));
-    size_t chunk = all_dev ? n : std::max<size_t>(1, (size_t(256) << 20) / (dim * 4));
-    for (size_t r0 = 0; r0 < n; r0 += chunk) {
-        size_t rows = std::min(chunk, n - r0);
-        InputView in; OutputView lo, ro;
-        VQB_TRY(in.bind(ctx, x + r0 * dim, rows * dim * 4));
-        VQB_TRY(lo.bind(ctx, leaf_out ? leaf_out + r0 : nullptr, rows * 4));
-        VQB_TRY(ro.bind(ctx, recon_out ? recon_out + r0 * dim : nullptr, rows * dim * 2));
-        const float* xd = static_cast<const float*>(in.dev);
-        uint32_t* ld = static_cast<uint32_t*>(lo.dev);
-        __half* rd = static_cast<__half*>(ro.dev);
+    // host inputs / outputs: row chunks over three streams (common.cuh), so arbitrarily large batches fit and the copies
+    // overlap the descent; device buffers: one asynchronous launch
+    ChunkIo io;
+    io.in = x; io.in_unit = dim * 4;
+    io.out0 = leaf_out; io.out0_unit = 4;
+    io.out1 = recon_out; io.out1_unit = dim * 2;
+    return vqb_chunk_pipeline(ctx, n, io, [&](const void* din, void* d0, void* d1, size_t rows, size_t) -> int {
+        const float* xd = static_cast<const float*>(din);
+        uint32_t* ld = static_cast<uint32_t*>(d0);
+        __half* rd = static_cast<__half*>(d1);
         unsigned grid = cdiv(rows, 8);
         static const bool old_enc = [] { const char* e = std::getenv("VQB_TSVQ_OLD_ENCODE"); return e && *e && *e != '0'; }();
         const size_t lm_smem = (size_t)TL_WARPS * dim * 4;
@@ -1067,11 +1064,8 @@ int vqb_tsvq_encode(vqb_tsvq* t, const float* x, size_t n, uint32_t* leaf_out, u
                 k_tsvq_encode<VQB_COSINE><<<grid, 256, 0, ctx->stream>>>(xd, rows, (int)dim, t->cent.as<float>(), t->left.as<int>(), t->right.as<int>(), ld, rd); break;
         }
         VQB_LAUNCHED(ctx);
-        VQB_TRY(lo.finish(ctx));
-        VQB_TRY(ro.finish(ctx));
-        if (!all_dev) VQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    return VQB_SUCCESS;
+        return VQB_SUCCESS;
+    });
 }
 
 }  // extern "C"
