@@ -55,6 +55,9 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-clock-probe", action="store_true", help="skip the 0.7 s untimed continuation (profiler runs)")
     p.add_argument("--no-paths", action="store_true", help="skip the per-path throughputs (BQ/SQ, Manhattan, L2 kinds, TSVQ)")
+    p.add_argument("--config", default=None, choices=["metric100M", "c2", "c5a", "c5b"],
+                   help="stated-scale run of one BASELINE config instead of the headline step: the full row count is streamed "
+                        "through the GPU(s) in device-generated chunks; prints one JSON line")
     return p.parse_args()
 
 
@@ -380,13 +383,93 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC_NAME, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"PQ encode {args.rows}x{DIM} f32 per GPU, m={M}, k={K}, {args.metric}", "rows_per_gpu": args.rows,
+        "config": {"workload": f"PQ encode {args.rows}x{DIM} f32/GPU m={M} k={K} {args.metric}", "rows_per_gpu": args.rows,
                    "dim": DIM, "m": M, "k": K, "distance": args.metric, "assign": args.assign,
-                   "l2": "input (3.07 GB) > L2 (126 MB)", "parallelism": f"rows sharded over {args.gpus} GPU(s), no collective",
-                   "rows_timed_per_step": rows},
+                   "l2": "input > L2", "parallelism": f"rows/{args.gpus}, no collective", "rows_timed_per_step": rows},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def run_config(args, rank, world, local):
+    """Stated-scale runs (BASELINE.json configs / the metric's 100M-vector target).  The input does not fit HBM, so it is
+    generated on the device chunk by chunk (torch's Philox generator) into one resident buffer; only the engine's kernels
+    are timed (CUDA events around each chunk's call on the engine stream, summed); rows are split evenly over the ranks,
+    no collective.  value = total rows / max-over-ranks kernel time."""
+    import torch
+    import vq_b200 as vq
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = vq.Engine(local)
+    ext = torch.cuda.ExternalStream(eng.stream, device=local)
+    lib = eng.lib
+    spec = {"metric100M": dict(rows=100_000_000, dim=768, m=96, chunk=4_000_000, metric="cosine", what="pq"),
+            "c5a": dict(rows=1_000_000_000, dim=128, m=16, chunk=16_000_000, metric="euclidean", what="pq"),
+            "c5b": dict(rows=10_000_000, dim=768, m=96, chunk=1_000_000, metric="manhattan", what="pq"),
+            "c2": dict(rows=100_000_000, dim=1536, m=0, chunk=2_000_000, metric="", what="bqsq")}[args.config]
+    rows_total, dim, chunk = spec["rows"], spec["dim"], spec["chunk"]
+    my_rows = rows_total // world + (1 if rank < rows_total % world else 0)
+    g = torch.Generator(device="cuda"); g.manual_seed(777 + rank)
+    buf = torch.empty(chunk, dim, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = {}
+
+    def timed(name, fn):
+        e0.record(ext); fn(); e1.record(ext); torch.cuda.synchronize()
+        ms[name] = ms.get(name, 0.0) + e0.elapsed_time(e1)
+
+    def fill(rows):
+        if spec["what"] == "pq":
+            centers = fill.centers
+            for r0 in range(0, rows, 500_000):
+                r1 = min(rows, r0 + 500_000)
+                ids = torch.randint(0, 1024, (r1 - r0,), device="cuda", generator=g)
+                buf[r0:r1] = centers[ids] + 0.25 * torch.randn(r1 - r0, dim, device="cuda", generator=g)
+        else:
+            for r0 in range(0, rows, 500_000):
+                buf[r0:min(rows, r0 + 500_000)].normal_(0.0, 0.5, generator=g)
+    if spec["what"] == "pq":
+        gc = torch.Generator(device="cuda"); gc.manual_seed(20240)
+        fill.centers = torch.randn(1024, dim, device="cuda", generator=gc)
+        fill(min(chunk, my_rows))
+        m_, d_ = spec["m"], dim // spec["m"]
+        sel = torch.randint(0, min(chunk, my_rows), (m_ * K,), device="cuda", generator=gc)     # same rows on every rank? no: same ids, rank-local data
+        cb = buf[sel].reshape(m_, K, m_, d_)
+        cb = torch.stack([cb[s_, :, s_, :] for s_ in range(m_)]).contiguous().cpu().numpy()
+        pq = vq.ProductQuantizer.from_codebooks(cb, vq.Distance(spec["metric"]), engine=eng)
+        codes = torch.empty(chunk, m_, dtype=torch.uint8, device="cuda")
+    else:
+        q = torch.empty(chunk, dim, dtype=torch.uint8, device="cuda")
+        step = np.float32(2.0) / np.float32(255.0)
+    done = 0
+    while done < my_rows:
+        rows = min(chunk, my_rows - done)
+        fill(rows)
+        torch.cuda.synchronize()
+        if spec["what"] == "pq":
+            timed("encode", lambda: eng.check(lib.vqb_pq_encode(pq._handle, buf.data_ptr(), rows, 0, codes.data_ptr(), 1, None)))
+        else:
+            ne = rows * dim
+            timed("bq", lambda: eng.check(lib.vqb_bq_quantize(eng.h, buf.data_ptr(), ne, 0.0, 0, 1, q.data_ptr())))
+            timed("sq8", lambda: eng.check(lib.vqb_sq_quantize(eng.h, buf.data_ptr(), ne, -1.0, 1.0, float(step), 256, q.data_ptr())))
+        done += rows
+    keys = sorted(ms)
+    t = torch.tensor([ms[k_] for k_ in keys], device="cuda")
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    if rank == 0:
+        res = {"config": args.config, "n_gpus": world, "rows_total": rows_total, "dim": dim, "chunk_rows": chunk,
+               "data": "synthetic, generated on the device per chunk", "unit": "Mvec/s",
+               "note": "kernel time only (CUDA events per chunk, summed, max over ranks); rows split evenly, no collective"}
+        for k_, v in zip(keys, t.tolist()):
+            res[k_] = {"value": rows_total / (v * 1e-3) / 1e6, "ms_total": v}
+        if spec["what"] == "pq":
+            res.update({"m": spec["m"], "k": K, "distance": spec["metric"]})
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        td.destroy_process_group()
 
 
 def main():
@@ -396,6 +479,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config:
+        run_config(args, rank, world, local)
         return
 
     import torch
@@ -477,16 +563,15 @@ def main():
                 "hbm": {"achieved": hbm_bytes / kern_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_bytes / kern_s / 1e9 / peaks["hbm_gbs"]},
                 "epilogue": {"floor_ms": epi_floor_s * 1e3, "frac": epi_floor_s / kern_s,
-                             "note": "scan-only floor, profiles/r02_ubench.txt (E)"}}
+                             "note": "scan floor, r02_ubench E"}}
 
     out = {
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"PQ encode {rows}x{DIM} f32 per GPU, m={M}, k={K}, {args.metric}", "rows_per_gpu": rows,
+        "config": {"workload": f"PQ encode {rows}x{DIM} f32/GPU m={M} k={K} {args.metric}", "rows_per_gpu": rows,
                    "dim": DIM, "m": M, "k": K, "distance": args.metric, "assign": args.assign,
-                   "l2": "input (3.07 GB) > L2 (126 MB)", "parallelism": f"rows sharded over {world} GPU(s), no collective",
-                   "rows_timed_per_step": rows},
+                   "l2": "input > L2", "parallelism": f"rows/{world}, no collective", "rows_timed_per_step": rows},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
     }
 
@@ -513,7 +598,7 @@ def main():
                 t = torch.tensor([dt], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX); dt = float(t.item())
             out["e2e"] = {"value": world * e_rows * n_e2e / dt / 1e6, "unit": UNIT,
                           "h2d_bytes_per_step": int(e_rows * DIM * 4), "d2h_bytes_per_step": int(e_rows * DIM * 2),
-                          "note": "pinned f32 in, f16 reconstruction out, 3-stream chunks"}
+                          "note": "pinned f32 in, f16 out"}
             del hx, hr
         except Exception as ex:  # never lose the primary line
             out["e2e"] = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
@@ -579,7 +664,7 @@ def main():
             out["kmeans"] = {"value": ran / t_full, "unit": "iter/s", "ms_per_iter": per_iter * 1e3,
                              "train_call_ms": t_full * 1e3, "overhead_ms": (t_full - ran * per_iter) * 1e3,
                              "iters": ran, "rows_total": n_total, "rows_per_gpu": n_loc, "scaling": "strong", "update": "fast",
-                             "collective": "ncclAllReduce by the library, 0.98 MB per iteration" if dist_on else "none",
+                             "collective": "nccl (library)" if dist_on else "none",
                              "roofline": {"bound": "hbm", "achieved": km_bytes / per_iter / 1e9 / world, "peak": peaks["hbm_gbs"],
                                           "unit": "GB/s", "frac": km_bytes / per_iter / 1e9 / world / peaks["hbm_gbs"],
                                           "tensor_frac": km_tf / peaks["bf16_tflops"]}}
@@ -602,7 +687,7 @@ def main():
         try:
             v, cores, kind, dt, backend = cpu_encode_rate(args.cpu_sample, args.metric)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                   "sample": f"{args.cpu_sample} of {rows} vectors ({dt:.1f} s), src/pq.rs:167-199 loop over all cores, {backend}"}
+                                   "sample": f"{args.cpu_sample} of {rows} vectors, {dt:.1f} s, pq.rs:167-199 loop; {backend}"[:90]}
             try:
                 shipped = cpu_as_shipped(args.metric)
                 print(json.dumps({"cpu_as_shipped": shipped}), flush=True)   # separate line: the reference's own parallelism
@@ -614,7 +699,16 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": repr(ex)[:200]}
 
     if rank == 0:
-        print(json.dumps(out))
+        def short(o):   # 5 significant digits everywhere: the line must fit the driver's tail
+            if isinstance(o, float):
+                return float(f"{o:.5g}")
+            if isinstance(o, dict):
+                return {k: short(v) for k, v in o.items()}
+            if isinstance(o, list):
+                return [short(v) for v in o]
+            return o
+        out["clocks"].pop("samples", None)
+        print(json.dumps(short(out), separators=(",", ":")))
     if dist_on:
         td.destroy_process_group()
 
