@@ -563,7 +563,7 @@ def main():
                 "hbm": {"achieved": hbm_bytes / kern_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_bytes / kern_s / 1e9 / peaks["hbm_gbs"]},
                 "epilogue": {"floor_ms": epi_floor_s * 1e3, "frac": epi_floor_s / kern_s,
-                             "note": "scan floor, r02_ubench E"}}
+                             "src": "r02_ubench E"}}
 
     out = {
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -598,7 +598,7 @@ def main():
                 t = torch.tensor([dt], device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX); dt = float(t.item())
             out["e2e"] = {"value": world * e_rows * n_e2e / dt / 1e6, "unit": UNIT,
                           "h2d_bytes_per_step": int(e_rows * DIM * 4), "d2h_bytes_per_step": int(e_rows * DIM * 2),
-                          "note": "pinned f32 in, f16 out"}
+                          "io": "pinned f32 in, f16 out"}
             del hx, hr
         except Exception as ex:  # never lose the primary line
             out["e2e"] = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
@@ -687,7 +687,7 @@ def main():
         try:
             v, cores, kind, dt, backend = cpu_encode_rate(args.cpu_sample, args.metric)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                   "sample": f"{args.cpu_sample} of {rows} vectors, {dt:.1f} s, pq.rs:167-199 loop; {backend}"[:90]}
+                                   "sample": f"{args.cpu_sample} of {rows} vectors, {dt:.1f} s, pq.rs:167-199 loop; {backend}"[:70]}
             try:
                 shipped = cpu_as_shipped(args.metric)
                 print(json.dumps({"cpu_as_shipped": shipped}), flush=True)   # separate line: the reference's own parallelism
