@@ -88,13 +88,15 @@ inline std::string get_simd_backend() { return vqb_backend_name(); }  // src/cor
 // ------------------------------------------------------------------------------------ Distance
 enum class Distance : int {  // enum order of src/core/distance.rs:8-17 == VQB_* ids
     SquaredEuclidean = VQB_SQUARED_EUCLIDEAN, Euclidean = VQB_EUCLIDEAN, Manhattan = VQB_MANHATTAN,
-    CosineDistance = VQB_COSINE
+    CosineDistance = VQB_COSINE,
+    Chebyshev = VQB_CHEBYSHEV   // EXTENSION: not in the reference; distance_compute and ProductQuantizer encoding only
 };
 inline const char* distance_name(Distance d) {  // distance.rs:21-29
     switch (d) {
         case Distance::SquaredEuclidean: return "squared_euclidean";
         case Distance::Euclidean: return "euclidean";
         case Distance::Manhattan: return "manhattan";
+        case Distance::Chebyshev: return "chebyshev";
         default: return "cosine";
     }
 }

@@ -51,6 +51,12 @@ extern "C" {
 #define VQB_EUCLIDEAN         1
 #define VQB_MANHATTAN         2
 #define VQB_COSINE            3
+/* EXTENSION, not part of the reference (its Distance has exactly the four kinds above, src/core/distance.rs:8-17):
+ * Chebyshev distance max_i |a_i - b_i| (components whose difference is NaN are skipped).  Accepted by
+ * vqb_distance_batch and by vqb_pq_create / vqb_pq_encode (CUDA-core assignment kernel); training is squared-L2 whatever
+ * the metric, as in the reference (src/pq.rs:121-132).  There is nothing in the reference to be parity-checked against:
+ * the tests compare with oracle/vq_oracle.c's restatement of this definition only. */
+#define VQB_CHEBYSHEV         5
 
 typedef struct vqb_ctx vqb_ctx;   /* one GPU, its streams and scratch memory          */
 typedef struct vqb_pq vqb_pq;     /* immutable trained ProductQuantizer (pq.rs:39-45) */

@@ -22,7 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvq_oracle.so")
 HSD_PATH = os.path.join(HERE, "_ref", "libhsd_ref.so")
 
-METRICS = {"squared_euclidean": 0, "euclidean": 1, "manhattan": 2, "cosine": 3}
+METRICS = {"squared_euclidean": 0, "euclidean": 1, "manhattan": 2, "cosine": 3,
+           "chebyshev": 5}   # 5: extension, not in the reference
 SEMS = {"scalar": 0, "avx512": 1, "avx2": 2, "hsdlib": 3}
 # hsdlib.h:57-68
 HSD_BACKENDS = {"auto": 0, "scalar": 1, "avx": 2, "avx2": 3, "avx512f": 4}

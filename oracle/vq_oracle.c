@@ -249,6 +249,11 @@ float vqo_distance(int metric, int sem, const float* a, const float* b, size_t n
     switch (metric) {
     case VQO_SQEUCLIDEAN: return sq_dispatch(sem, a, b, n);
     case VQO_EUCLIDEAN:   return sqrtf(sq_dispatch(sem, a, b, n)); /* distance.rs:58 */
+    case VQO_CHEBYSHEV: {   /* EXTENSION, no reference counterpart: max_i |a_i - b_i|, NaN differences skipped */
+        float mx = 0.0f;
+        for (size_t i = 0; i < n; ++i) { float v = fabsf(a[i] - b[i]); if (v > mx) mx = v; }
+        return mx;
+    }
     case VQO_MANHATTAN:                                              /* distance.rs:86-95 */
         if (sem == VQO_SEM_HSDLIB && g_hsd_l1) { if (g_hsd_l1(a, b, n, &r) == 0) return r; }
         else if (sem != VQO_SEM_SCALAR) { if (vqo_hsd_manhattan(sem, a, b, n, &r) == 0) return r; }

@@ -27,7 +27,8 @@ extern "C" {
 #endif
 
 /* Distance metric ids == enum order of src/core/distance.rs:8-17 */
-enum { VQO_SQEUCLIDEAN = 0, VQO_EUCLIDEAN = 1, VQO_MANHATTAN = 2, VQO_COSINE = 3 };
+enum { VQO_SQEUCLIDEAN = 0, VQO_EUCLIDEAN = 1, VQO_MANHATTAN = 2, VQO_COSINE = 3,
+       VQO_CHEBYSHEV = 5 /* EXTENSION: not in the reference (distance.rs:8-17); restated definition only, parity n/a */ };
 
 /* Which build of the reference the distance follows.
  *   SCALAR : `simd` feature off  -> Rust loops, src/core/distance.rs:75-83,93-95,106-119

@@ -252,6 +252,34 @@ def test_pq_train_reseed_and_early_exit(vq, oracle):
     assert np.array_equal(pq0.codebooks[1], x[init[1].astype(int), 4:])
 
 
+def test_chebyshev_extension_bit_exact(vq, oracle):
+    """EXTENSION (north_star names a Chebyshev assignment; the reference has no such metric, src/core/distance.rs:8-17):
+    parity is against the oracle's restated definition only."""
+    rng = np.random.default_rng(9)
+    d = vq.Distance.chebyshev()
+    with pytest.raises(ValueError):
+        vq.Distance("chebyshev")           # the reference's constructor knows four kinds
+    for n in (1, 7, 8, 33, 1536):
+        a = (rng.standard_normal((64, n)) * rng.choice([1e-3, 1.0, 1e3], (64, 1))).astype(F)
+        b = rng.standard_normal((64, n)).astype(F)
+        a[0] = 0; b[1] = 0; a[3] = b[3]; a[4, 0] = np.nan; b[5, -1] = np.inf
+        got = d.compute_batch(a, b)
+        want = np.array([oracle.distance("chebyshev", a[i], b[i]) for i in range(64)], F)
+        assert np.array_equal(bits(got), bits(want)), n
+    for dim, m, k in ((64, 8, 256), (96, 3, 50), (40, 8, 256), (128, 8, 300)):
+        n = 3000
+        x = mixture(n, dim, 41)
+        sd = dim // m
+        cb = np.stack([x[rng.choice(n, k, replace=False), s * sd:(s + 1) * sd] for s in range(m)]).astype(F)
+        cb[0, 3] = cb[0, 1]          # duplicate: lowest index wins (pq.rs:183-191)
+        x[1, :sd] = np.nan
+        pq = vq.ProductQuantizer.from_codebooks(cb, d)
+        codes, recon = pq.encode_with_recon(x)
+        want_codes, want_recon = oracle.pq_encode(cb, "chebyshev", x)
+        assert np.array_equal(codes.astype(np.uint32), want_codes)
+        assert np.array_equal(bits(recon), bits(want_recon))
+
+
 # ------------------------------------------------------------------ PQ: encode
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("dim,m,k", [(64, 8, 256), (128, 8, 256), (96, 3, 50), (40, 8, 256)])

@@ -345,3 +345,19 @@ def test_recon_mse(oracle):
     x = np.array([1.0, 2.0, 3.0, 4.0], F)
     r = np.array([1.0, 2.0, 3.0, 6.0], np.float16)
     assert oracle.recon_mse(x, r) == 1.0
+
+
+def test_chebyshev_extension_definition(oracle):
+    """EXTENSION (VQB_CHEBYSHEV): the reference has no such metric (src/core/distance.rs:8-17), so there is no reference
+    value to pin against -- these hand-computed cases pin the restated definition max_i |a_i - b_i| (NaN differences skipped)
+    that the GPU path is compared with."""
+    f = lambda a, b: oracle.distance("chebyshev", np.asarray(a, np.float32), np.asarray(b, np.float32))
+    assert f([1, 2, 3], [4, 0, 3.5]) == 3.0
+    assert f([1, 2, 3], [1, 2, 3]) == 0.0
+    assert f([], []) == 0.0
+    assert f([-5.5], [2.25]) == 7.75
+    assert f([np.nan, 1.0], [0.0, 3.0]) == 2.0            # NaN difference skipped
+    assert f([np.inf, 1.0], [0.0, 3.0]) == np.inf
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(257).astype(np.float32), rng.standard_normal(257).astype(np.float32)
+    assert f(a, b) == np.abs(a - b).max()

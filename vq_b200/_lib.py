@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(HERE, "libvqb200.so")
 SUCCESS, ERR_NULL_PTR, ERR_EMPTY_INPUT, ERR_INVALID_INPUT = 0, -1, -2, -3
 ERR_UNSUPPORTED_DEVICE, ERR_DIM_MISMATCH, FAILURE = -4, -5, -99
 
-METRIC_IDS = {"squared_euclidean": 0, "euclidean": 1, "manhattan": 2, "cosine": 3}
+METRIC_IDS = {"squared_euclidean": 0, "euclidean": 1, "manhattan": 2, "cosine": 3,
+              "chebyshev": 5}   # 5 = VQB_CHEBYSHEV: extension, not in the reference
 UPDATE_ORDERED, UPDATE_FAST = 0, 1
 ASSIGN_AUTO, ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1, 2
 TRAIN_USE_COMM = 1

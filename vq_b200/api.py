@@ -130,13 +130,17 @@ _engines: dict[int, Engine] = {}
 _engines_lock = threading.Lock()
 
 
-def default_engine() -> Engine:
+def default_engine(like=None) -> Engine:
+    """The process-wide engine of a device: the device of `like` when it is a CUDA tensor, else torch's current device
+    (LOCAL_RANK without torch)."""
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     if torch is not None and torch.cuda.is_available():
         try:
             dev = torch.cuda.current_device()
         except Exception:
             pass
+    if like is not None and torch is not None and isinstance(like, torch.Tensor) and like.is_cuda:
+        dev = like.device.index
     with _engines_lock:
         if dev not in _engines:
             _engines[dev] = Engine(dev)
@@ -173,6 +177,14 @@ def _order_after_torch(t):
             es = torch.cuda.ExternalStream(e.stream, device=t.device)
             if es.cuda_stream != cur.cuda_stream:
                 es.wait_stream(cur)
+
+
+def _same_device(eng, *arrays):
+    """A CUDA tensor must live on the engine's GPU: the library only checks that a pointer is device memory, not whose."""
+    for a in arrays:
+        if _is_torch(a) and a.is_cuda and a.device.index != eng.device:
+            raise ValueError(f"tensor on cuda:{a.device.index} passed to the engine of cuda:{eng.device}")
+    return eng
 
 
 def _in(a, dtype):
@@ -239,6 +251,15 @@ class Distance:
     def cosine():
         return Distance("cosine")
 
+    @staticmethod
+    def chebyshev():
+        """EXTENSION, not in pyvq (the reference's Distance has four kinds, src/core/distance.rs:8-17): max_i |a_i - b_i|.
+        Reachable through this method only -- Distance("chebyshev") raises like the reference does.  Usable for
+        Distance.compute and ProductQuantizer encoding (CUDA-core assignment kernel); TSVQ rejects it."""
+        d = Distance("manhattan")
+        d.metric = "chebyshev"
+        return d
+
     @property
     def id(self) -> int:
         return _lib.METRIC_IDS[self.metric]
@@ -254,7 +275,7 @@ class Distance:
         return float(self.compute_batch(a[None, :], b[None, :], engine)[0])
 
     def compute_batch(self, a, b, engine: Engine | None = None):
-        eng = engine or default_engine()
+        eng = _same_device(engine or default_engine(a), a, b)
         pa, ka, _ = _in(a, np.float32)
         pb, kb, _ = _in(b, np.float32)
         if tuple(ka.shape) != tuple(kb.shape):
@@ -292,7 +313,7 @@ class BinaryQuantizer:
     high = property(lambda self: self._high)
 
     def quantize(self, values):
-        eng = self._engine or default_engine()
+        eng = _same_device(self._engine or default_engine(values), values)
         p, keep, _ = _in(values, np.float32)
         po, out = _out_like(values, tuple(keep.shape), np.uint8)
         n = int(np.prod(keep.shape))
@@ -301,7 +322,7 @@ class BinaryQuantizer:
         return out
 
     def dequantize(self, codes):
-        eng = self._engine or default_engine()
+        eng = _same_device(self._engine or default_engine(codes), codes)
         p, keep, _ = _in(codes, np.uint8)
         po, out = _out_like(codes, tuple(keep.shape), np.float32)
         eng.check(eng.lib.vqb_bq_dequantize(eng.h, p, int(np.prod(keep.shape)), self._low, self._high, po))
@@ -338,7 +359,7 @@ class ScalarQuantizer:
     step = property(lambda self: float(self._step))
 
     def quantize(self, values):
-        eng = self._engine or default_engine()
+        eng = _same_device(self._engine or default_engine(values), values)
         p, keep, _ = _in(values, np.float32)
         po, out = _out_like(values, tuple(keep.shape), np.uint8)
         eng.check(eng.lib.vqb_sq_quantize(eng.h, p, int(np.prod(keep.shape)), float(self._min), float(self._max),
@@ -347,7 +368,7 @@ class ScalarQuantizer:
         return out
 
     def dequantize(self, codes):
-        eng = self._engine or default_engine()
+        eng = _same_device(self._engine or default_engine(codes), codes)
         p, keep, _ = _in(codes, np.uint8)
         po, out = _out_like(codes, tuple(keep.shape), np.float32)
         eng.check(eng.lib.vqb_sq_dequantize(eng.h, p, int(np.prod(keep.shape)), float(self._min),
@@ -411,7 +432,7 @@ class ProductQuantizer:
             raise InvalidParameter("k", f"not enough data points ({n}) for {k} clusters")
         self._m, self._k, self._dim, self._sub_dim = m, k, dim, dim // m
         self._distance = distance or Distance.euclidean()  # pyvq/src/pq.rs:73-75
-        self._engine = eng = engine or default_engine()
+        self._engine = eng = _same_device(engine or default_engine(training_data), training_data)
         self._handle = None
 
         if init_idx is None:
@@ -499,7 +520,7 @@ class ProductQuantizer:
 
     # ---- batch API ---------------------------------------------------------------------------
     def _encode(self, x, want_codes, want_recon, assign="auto"):
-        eng = self._engine
+        eng = _same_device(self._engine, x)
         px, keep, _ = _in(x, np.float32)
         if keep.ndim != 2 or keep.shape[1] != self._dim:
             raise DimensionMismatch(self._dim, keep.shape[-1] if keep.ndim else 0)
@@ -524,7 +545,7 @@ class ProductQuantizer:
         return self._encode(x, True, True, assign)
 
     def decode(self, codes):
-        eng = self._engine
+        eng = _same_device(self._engine, codes)
         cdt = np.uint8 if self._k <= 256 else (np.uint16 if self._k <= 65536 else np.uint32)
         pc, keep, _ = _in(codes, cdt)
         n = keep.shape[0]
@@ -551,7 +572,7 @@ class TSVQ:
             raise ValueError("Training data cannot be empty")
         self._dim = shape[1]
         self._distance = distance or Distance.euclidean()
-        self._engine = eng = engine or default_engine()
+        self._engine = eng = _same_device(engine or default_engine(training_data), training_data)
         px, keep, _ = _in(training_data, np.float32)
         h = C.c_void_p()
         eng.check(eng.lib.vqb_tsvq_train(eng.h, px, shape[0], shape[1], int(max_depth), self._distance.id, C.byref(h)))
@@ -598,7 +619,7 @@ class TSVQ:
         return dict(centroids=cent, left=left, right=right, split_dim=sd, median=med, count=cnt)
 
     def _encode(self, x, want_leaf, want_recon):
-        eng = self._engine
+        eng = _same_device(self._engine, x)
         px, keep, _ = _in(x, np.float32)
         if keep.ndim != 2 or keep.shape[1] != self._dim:
             raise DimensionMismatch(self._dim, keep.shape[-1] if keep.ndim else 0)

@@ -301,4 +301,4 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n
 constexpr size_t VQB_TC_MIN_ROWS = 1024;
 
 // metric_kind for the exact kernel: the four Distance variants + the training distance
-enum { MK_SQEUCLID = 0, MK_EUCLID = 1, MK_MANHATTAN = 2, MK_COSINE = 3, MK_TRAIN = 4 };
+enum { MK_SQEUCLID = 0, MK_EUCLID = 1, MK_MANHATTAN = 2, MK_COSINE = 3, MK_TRAIN = 4, MK_CHEBYSHEV = 5 };

@@ -245,6 +245,15 @@ VQB_DEV float vq_distance(int metric, const A& a, const B& b, int n) {
         float s = hsd_sqeuclid<N>(a, b, n, ok);
         if (!ok) s = dist2_seq<N>(a, b, n);  // distance.rs:75-83 has the same order as distance2
         return metric == 1 ? __fsqrt_rn(s) : s;
+    } else if (metric == 5) {
+        // EXTENSION (VQB_CHEBYSHEV, no reference counterpart): max_i |a_i - b_i|, NaN differences skipped
+        float mx = 0.0f;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float v = fabsf(__fsub_rn(a(i), b(i)));
+            if (v > mx) mx = v;
+        }
+        return mx;
     } else if (metric == 2) {
         // n < 16: hsdlib's kernel is its scalar tail only (manhattan.c:132-163), i.e. the same sequential sum as
         // the Rust fallback it defers to on NaN/Inf -- one formula for every input, no per-element checks

@@ -240,7 +240,7 @@ int vqb_f16_dequantize(vqb_ctx* ctx, const uint16_t* q, size_t n, float* out) {
 int vqb_distance_batch(vqb_ctx* ctx, int metric, const float* a, const float* b, size_t rows, size_t n,
                        float* out) {
     if (!ctx) return VQB_ERR_NULL_PTR;
-    if (metric < 0 || metric > 3) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric %d", metric);
+    if ((metric < 0 || metric > 3) && metric != VQB_CHEBYSHEV) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric %d", metric);
     if (rows == 0) return VQB_SUCCESS;
     if (!out || (n && (!a || !b))) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null data pointer");
     if (n > (size_t)INT32_MAX) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "vector too long");

@@ -180,6 +180,7 @@ int vqb_pq_assign_exact_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, s
         case MK_MANHATTAN: return launch_mk<MK_MANHATTAN>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
         case MK_COSINE: return launch_mk<MK_COSINE>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
         case MK_TRAIN: return launch_mk<MK_TRAIN>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
+        case MK_CHEBYSHEV: return launch_mk<MK_CHEBYSHEV>(ctx, x, n, dim, k, d, cb, sub_list, n_sub, codes, code_bytes, stride_row, stride_sub, recon, n_sub_dev, go);
     }
     return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric kind %d", mk);
 }

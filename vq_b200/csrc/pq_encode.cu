@@ -104,7 +104,7 @@ int vqb_pq_create(vqb_ctx* ctx, const float* codebooks, size_t m, size_t k, size
     *out = nullptr;
     if (!codebooks) return vqb_fail(ctx, VQB_ERR_NULL_PTR, "null codebooks");
     if (m == 0 || k == 0 || sub_dim == 0) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "m, k, sub_dim must be > 0");
-    if (metric < 0 || metric > 3) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric %d", metric);
+    if ((metric < 0 || metric > 3) && metric != VQB_CHEBYSHEV) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "unknown metric %d", metric);
     std::lock_guard<std::mutex> lk(ctx->mu);
     VQB_CUDA(ctx, cudaSetDevice(ctx->device));
     vqb_pq* p = new vqb_pq();
@@ -112,7 +112,7 @@ int vqb_pq_create(vqb_ctx* ctx, const float* codebooks, size_t m, size_t k, size
     size_t bytes = m * k * sub_dim * sizeof(float);
     cudaError_t e = p->cb.alloc(bytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->cb.p, codebooks, bytes, cudaMemcpyDefault, ctx->stream);
-    if (e == cudaSuccess && metric != VQB_MANHATTAN && sub_dim == 8 && k <= 256) {
+    if (e == cudaSuccess && metric != VQB_MANHATTAN && metric != VQB_CHEBYSHEV && sub_dim == 8 && k <= 256) {
         e = p->tc_prep.alloc(vqb_tc_prep_bytes(m));
         if (e == cudaSuccess && vqb_tc_prepare(ctx, metric, p->cb.as<float>(), m, k, p->tc_prep.p) == VQB_SUCCESS)
             p->tc_ready = true;
