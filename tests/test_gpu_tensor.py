@@ -95,13 +95,16 @@ def test_tensor_scores_within_margin(eng, scale):
 
 
 @pytest.mark.parametrize("n,dim,m,k", [(1024, 32, 4, 256), (5000, 64, 8, 256), (4097, 40, 5, 256), (3000, 96, 12, 100),
-                                       (2500, 8, 1, 16), (20_000, 768, 96, 256), (1500, 24, 3, 7)])
+                                       (2500, 8, 1, 16), (20_000, 768, 96, 256), (1500, 24, 3, 7),
+                                       # sub_dim 16 (BASELINE config 1), 24 (the reference's eval default, 384 / 16), 32
+                                       (5000, 128, 8, 256), (3000, 384, 16, 256), (2500, 96, 3, 100), (4097, 48, 2, 256),
+                                       (2048, 64, 2, 33), (1500, 80, 5, 256), (1200, 24, 1, 9), (20_000, 384, 16, 256)])
 def test_tensor_train_assign_equals_exact_and_oracle(eng, oracle, n, dim, m, k):
     x = mixture(n, dim, n)
     cb = sample_codebooks(x, m, k, 1)
     cb[0, min(5, k - 1)] = cb[0, 2]      # duplicate centroid: lowest index must win (vector.rs:354-361)
     x[3] = x[2]                          # duplicate rows
-    x[10, :8] = cb[0, 2]                 # a row that sits exactly on the duplicated centroid
+    x[10, :dim // m] = cb[0, 2]          # a row that sits exactly on the duplicated centroid
     x[11] = 0.0
     x[12, 0] = np.nan                    # NaN distance at every centroid: index 0 sticks
     x[13, 3] = np.inf
@@ -117,14 +120,15 @@ def test_tensor_train_assign_equals_exact_and_oracle(eng, oracle, n, dim, m, k):
 
 
 @pytest.mark.parametrize("metric", ["squared_euclidean", "euclidean", "cosine"])
-@pytest.mark.parametrize("n,dim,m,k", [(4000, 64, 8, 256), (3001, 40, 5, 50), (10_000, 768, 96, 256)])
+@pytest.mark.parametrize("n,dim,m,k", [(4000, 64, 8, 256), (3001, 40, 5, 50), (10_000, 768, 96, 256),
+                                       (4000, 128, 8, 256), (3001, 384, 16, 256), (2500, 96, 3, 50), (10_000, 1536, 96, 256)])
 def test_tensor_encode_equals_exact_and_oracle(vq, oracle, metric, n, dim, m, k):
     x = mixture(n, dim, 31)
     cb = sample_codebooks(x, m, k, 32)
     cb[0, 3] = cb[0, 1]          # duplicate
     cb[m - 1, 0] = 0.0           # zero centroid (cosine zero rules, cosine.c:38-45)
     x[0] = 0.0                   # zero vector
-    x[1, :8] = np.nan            # NaN sub-vector: index 0 sticks (pq.rs:183-191)
+    x[1, :dim // m] = np.nan     # NaN sub-vector: index 0 sticks (pq.rs:183-191)
     x[2, 0] = np.inf
     x[3] = -x[4]                 # anti-correlated pair (cosine range [0, 2])
     x[5] = 3e19
@@ -169,7 +173,7 @@ def test_tensor_unsafe_codebook_falls_back_per_row(vq, eng):
 
 def test_tensor_mode_rejects_unsupported_shapes(vq):
     x = mixture(2000, 64, 1)
-    pq = vq.ProductQuantizer.from_codebooks(sample_codebooks(x, 4, 32, 2), vq.Distance.euclidean())  # sub_dim 16
+    pq = vq.ProductQuantizer.from_codebooks(sample_codebooks(x, 16, 32, 2), vq.Distance.euclidean())  # sub_dim 4
     with pytest.raises(ValueError):
         pq.encode(x, assign="tensor")
     pq = vq.ProductQuantizer.from_codebooks(sample_codebooks(x, 8, 32, 2), vq.Distance.manhattan())

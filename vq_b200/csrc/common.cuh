@@ -282,10 +282,10 @@ int vqb_assign_l1_tiles_launch(vqb_ctx* ctx, const float* x, size_t n, size_t di
                                void* codes, uint32_t code_bytes, size_t code_stride_row, size_t code_stride_sub, __half* recon);
 
 // tensor-core (tcgen05) GEMM-form assignment, pq_tc.cu.  `prep` is a device workspace of
-// vqb_tc_prep_bytes(m) bytes filled by vqb_tc_prepare from the current codebooks.
-size_t vqb_tc_prep_bytes(size_t m);
+// vqb_tc_prep_bytes(m, sub_dim) bytes filled by vqb_tc_prepare from the current codebooks.  sub_dim 8, 16, 24 or 32.
+size_t vqb_tc_prep_bytes(size_t m, size_t sub_dim);
 bool vqb_tc_supported(int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k, size_t sub_dim);
-int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t m, size_t k, void* prep,
+int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t m, size_t k, size_t sub_dim, void* prep,
                    const uint32_t* go = nullptr);
 // the 2-D tensor map over a row-major f32 matrix x[n, dim] used by the TMA-fed kernels: box = box_cols floats x 128 rows
 // (32 columns: SWIZZLE_128B, one 128-byte line per row; otherwise unswizzled rows of box_cols floats)

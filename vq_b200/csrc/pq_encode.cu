@@ -75,7 +75,7 @@ int encode_device(vqb_pq* pq, const float* x, size_t n, uint32_t assign_mode, vo
     const bool tc_ok = pq->tc_ready && vqb_tc_supported(pq->metric, x, n, dim, pq->m, pq->k, pq->d);
     if (assign_mode == VQB_ASSIGN_TENSOR && !tc_ok)
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT,
-                        "tensor-core assignment needs sub_dim 8, k <= 256, a non-Manhattan metric and 16-byte aligned rows");
+                        "tensor-core assignment needs sub_dim 8, 16, 24 or 32, k <= 256, a contraction metric and 16-byte aligned rows");
     const bool use_tc = tc_ok && (assign_mode == VQB_ASSIGN_TENSOR || (assign_mode == VQB_ASSIGN_AUTO && n >= VQB_TC_MIN_ROWS));
     cudaStream_t saved = ctx->stream;
     if (stream_override) ctx->stream = stream_override;
@@ -112,9 +112,10 @@ int vqb_pq_create(vqb_ctx* ctx, const float* codebooks, size_t m, size_t k, size
     size_t bytes = m * k * sub_dim * sizeof(float);
     cudaError_t e = p->cb.alloc(bytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->cb.p, codebooks, bytes, cudaMemcpyDefault, ctx->stream);
-    if (e == cudaSuccess && metric != VQB_MANHATTAN && metric != VQB_CHEBYSHEV && sub_dim == 8 && k <= 256) {
-        e = p->tc_prep.alloc(vqb_tc_prep_bytes(m));
-        if (e == cudaSuccess && vqb_tc_prepare(ctx, metric, p->cb.as<float>(), m, k, p->tc_prep.p) == VQB_SUCCESS)
+    if (e == cudaSuccess && metric != VQB_MANHATTAN && metric != VQB_CHEBYSHEV && k <= 256 &&
+        (sub_dim == 8 || sub_dim == 16 || sub_dim == 24 || sub_dim == 32)) {
+        e = p->tc_prep.alloc(vqb_tc_prep_bytes(m, sub_dim));
+        if (e == cudaSuccess && vqb_tc_prepare(ctx, metric, p->cb.as<float>(), m, k, sub_dim, p->tc_prep.p) == VQB_SUCCESS)
             p->tc_ready = true;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

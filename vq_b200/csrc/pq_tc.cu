@@ -48,13 +48,11 @@
 
 namespace {
 
-constexpr int TC_D = 8;            // sub_dim handled here
-constexpr int TC_G = 4;            // subspaces per CTA (4 * 8 floats = 128 B)
 constexpr int TC_N = 256;          // MMA N = centroid slots per subspace
 constexpr int TC_ROWS = 128;       // MMA M = rows per tile = TMEM lanes
 constexpr int RAW_STAGES = 3;      // TMA -> everyone: raw fp32 row tiles (128 rows x 128 B, SWIZZLE_128B)
 constexpr int AT_STAGES = 2;       // splitter -> MMA: x_lo tiles, same shape and swizzle as the raw tile
-constexpr int MG_STAGES = 2;       // splitter -> scan: margins of one row tile, [TC_G][128 rows]
+constexpr int MG_STAGES = 2;       // splitter -> scan: margins of one row tile, [G][128 rows]
 constexpr int RES_STAGES = 4;      // scan -> resolve: per-row candidate group of one unit
 constexpr int TC_THREADS = 640;    // 5 warpgroups: control | 2 helpers (split + resolve) | 2 scan (one per TMEM accumulator)
 // setmaxnreg budget: the pool is what the CTA was launched with (640 threads x 96 registers = 61440), so
@@ -64,34 +62,47 @@ static_assert(128 * REGS_CTRL + 256 * REGS_HELP + 256 * REGS_SCAN <= TC_THREADS 
               "setmaxnreg budget exceeds the registers the CTA owns");
 
 constexpr uint32_t RAW_BYTES = TC_ROWS * 128;           // 16 KB per stage
-constexpr uint32_t BP_CHUNKS = 5;                       // hi0 hi1 lo0 lo1 norm; the norm MMA's second K chunk is the
-                                                        // next row group's hi0 (finite) times the ones tile's zeros
-constexpr uint32_t BP_SBO = BP_CHUNKS * 128;            // 640 B between 8-row groups
-constexpr uint32_t BP_BYTES = 32 * BP_SBO;              // 20 KB: [32 row groups][5 k-chunks][8 rows][16 B]
 constexpr uint32_t BP_PAD = 128;                        // zeros behind the last image (read by the last norm chunk pair)
-constexpr uint32_t CB_BYTES = TC_N * TC_D * 4;          // 8 KB raw f32 codebook, row-major
 constexpr uint32_t AUX_BYTES = TC_N * 8;                // 2 KB (nb, sb) per centroid (cosine, exact path)
 constexpr uint32_t RINV_BYTES = TC_N * 4;               // 1 KB per centroid: -1/||c|| (cosine) or ||c||^2 (L2 kinds), fp32 re-score
 constexpr uint32_t ONES_BYTES = 16 * 2 * 128;           // 4 KB: [16 row groups][2 k-chunks][8 rows][16 B]
-constexpr uint32_t MG_BYTES = TC_G * TC_ROWS * 8;       // float2 {H, M} per (subspace, row)
 constexpr uint32_t RES_BYTES = TC_ROWS * 8;             // float2 {row minimum, M | group index} per row
-constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES + RINV_BYTES;  // per-subspace prepared image in HBM
-
-constexpr uint32_t OFF_RAW = 0;
-constexpr uint32_t OFF_AT = OFF_RAW + RAW_STAGES * RAW_BYTES;
-constexpr uint32_t OFF_BP = OFF_AT + AT_STAGES * RAW_BYTES;
-constexpr uint32_t OFF_CB = OFF_BP + TC_G * BP_BYTES + BP_PAD;
-constexpr uint32_t OFF_AUX = OFF_CB + TC_G * CB_BYTES;
-constexpr uint32_t OFF_RINV = OFF_AUX + TC_G * AUX_BYTES;
-constexpr uint32_t OFF_ONES = OFF_RINV + TC_G * RINV_BYTES;
-constexpr uint32_t OFF_MG = OFF_ONES + ONES_BYTES;
-constexpr uint32_t OFF_RES = OFF_MG + MG_STAGES * MG_BYTES;
-constexpr uint32_t OFF_SINFO = OFF_RES + RES_STAGES * RES_BYTES;  // TC_G x {sqrt(cmax2), unsafe}
-constexpr uint32_t OFF_BAR = OFF_SINFO + 64;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // barriers + slack for the 1024-byte alignment
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
-static_assert(OFF_AT % 1024 == 0 && OFF_BP % 128 == 0 && OFF_CB % 128 == 0 && OFF_ONES % 128 == 0, "operand tiles must be aligned");
 constexpr uint32_t RES_AMBIGUOUS = 0x80000000u;         // sign bit of the margin word
+
+// Everything that depends on the sub-vector length D (8, 16, 24 or 32 floats).  A CTA owns the G subspaces that share one
+// 128-byte line of each row (D = 24: one subspace, the last 32 bytes of the line belong to its neighbour and are ignored);
+// a unit's scores are KC = D / 8 chained K = 8 MMAs per term.
+template <int D>
+struct Cfg {
+    static_assert(D == 8 || D == 16 || D == 24 || D == 32, "sub_dim handled by the tensor kernel");
+    static constexpr int G = (D == 24) ? 1 : 32 / D;          // subspaces per CTA
+    static constexpr int KC = D / 8;                          // K = 8 MMAs per operand term
+    static constexpr int NCH = D / 4;                         // 16-byte chunks per sub-vector / centroid
+    // B image of one subspace: [32 row groups][2 NCH + 1 k-chunks: hi.. lo.. norm][8 rows][16 B]; the norm MMA's second
+    // K chunk is the next row group's first hi chunk (finite) times the ones tile's zeros
+    static constexpr uint32_t BP_CHUNKS = 2 * NCH + 1;
+    static constexpr uint32_t BP_SBO = BP_CHUNKS * 128;       // bytes between 8-row groups
+    static constexpr uint32_t BP_BYTES = 32 * BP_SBO;
+    static constexpr uint32_t CB_BYTES = TC_N * D * 4;        // raw f32 codebook, row-major
+    static constexpr uint32_t MG_BYTES = G * TC_ROWS * 8;     // float2 {H, M} per (subspace, row)
+    static constexpr uint32_t PREP_BYTES = BP_BYTES + CB_BYTES + AUX_BYTES + RINV_BYTES;  // per-subspace prepared image in HBM
+    static constexpr uint32_t OFF_RAW = 0;
+    static constexpr uint32_t OFF_AT = OFF_RAW + RAW_STAGES * RAW_BYTES;
+    static constexpr uint32_t OFF_BP = OFF_AT + AT_STAGES * RAW_BYTES;
+    static constexpr uint32_t OFF_CB = OFF_BP + G * BP_BYTES + BP_PAD;
+    static constexpr uint32_t OFF_AUX = OFF_CB + G * CB_BYTES;
+    static constexpr uint32_t OFF_RINV = OFF_AUX + G * AUX_BYTES;
+    static constexpr uint32_t OFF_ONES = OFF_RINV + G * RINV_BYTES;
+    static constexpr uint32_t OFF_MG = OFF_ONES + ONES_BYTES;
+    static constexpr uint32_t OFF_RES = OFF_MG + MG_STAGES * MG_BYTES;
+    static constexpr uint32_t OFF_SINFO = OFF_RES + RES_STAGES * RES_BYTES;  // G x {sqrt(cmax2), unsafe}
+    static constexpr uint32_t OFF_BAR = OFF_SINFO + 64;
+    static constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // barriers + slack for the 1024-byte alignment
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+    static_assert(OFF_AT % 1024 == 0 && OFF_BP % 128 == 0 && OFF_CB % 128 == 0 && OFF_ONES % 128 == 0, "operand tiles must be aligned");
+};
+// the prepared images of all sub_dims share one size formula on the host side
+constexpr size_t prep_bytes_of(size_t d) { return 32 * ((2 * (d / 4) + 1) * 128) + TC_N * d * 4 + AUX_BYTES + RINV_BYTES; }
 
 template <int D>
 struct RegArr {
@@ -235,16 +246,19 @@ __device__ __forceinline__ float tf32_lo(float v) {  // v - trunc_tf32(v): exact
 // ------------------------------------------------------------------------------- prepare kernel
 // One CTA per subspace, thread j = centroid slot j.  Builds the B operand tile
 // [c_hi | c_lo | norm pieces] in its shared-memory image, a raw f32 copy and the cosine norms.
-template <int MK>
+template <int MK, int TC_D>
 __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ codebooks, int k, uint8_t* __restrict__ prep,
                                                       SubInfo* __restrict__ sinfo, const uint32_t* __restrict__ go) {
     __shared__ float red[TC_N];
     __shared__ uint32_t bad;
     if (go && *go == 0) return;
+    using C = Cfg<TC_D>;
+    constexpr uint32_t BP_SBO = C::BP_SBO, BP_BYTES = C::BP_BYTES, CB_BYTES = C::CB_BYTES;
+    constexpr int NCH = C::NCH;
     const int s = blockIdx.x, j = threadIdx.x;
     if (j == 0) bad = 0;
     __syncthreads();
-    uint8_t* img = prep + (size_t)s * PREP_BYTES;
+    uint8_t* img = prep + (size_t)s * C::PREP_BYTES;
     float c[TC_D];
     const bool real = j < k;
 #pragma unroll
@@ -284,14 +298,15 @@ __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ c
     }
     // B' image: row j, 16-byte k-chunk q at (j/8)*BP_SBO + q*128 + (j%8)*16
     float4* row = reinterpret_cast<float4*>(img + (j >> 3) * BP_SBO + (j & 7) * 16);
-    row[0 * 8] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    row[1 * 8] = make_float4(hi[4], hi[5], hi[6], hi[7]);
-    row[2 * 8] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-    row[3 * 8] = make_float4(lo[4], lo[5], lo[6], lo[7]);
-    row[4 * 8] = make_float4(npiece[0], npiece[1], npiece[2], 0.f);
-    float4* raw = reinterpret_cast<float4*>(img + BP_BYTES + j * 32);
-    raw[0] = make_float4(c[0], c[1], c[2], c[3]);
-    raw[1] = make_float4(c[4], c[5], c[6], c[7]);
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+        row[q * 8] = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        row[(NCH + q) * 8] = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+    row[2 * NCH * 8] = make_float4(npiece[0], npiece[1], npiece[2], 0.f);
+    float4* raw = reinterpret_cast<float4*>(img + BP_BYTES + j * (TC_D * 4));
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) raw[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
     {   // cosine norms exactly as hsd_sim_cosine_f32 accumulates them (cosine.c:163-198)
         bool tok;
         RegArr<TC_D> ca;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(TC_N) k_tc_prepare(const float* __restrict__ c
 
 // ---------------------------------------------------------------------------- exact evaluation
 // The reference's distance between the row's sub-vector (registers) and centroid j (shared memory).
-template <int MK>
+template <int MK, int TC_D>
 struct ExactEval {
     RegArr<TC_D> x;
     float na, sa;
@@ -379,8 +394,15 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf
 // Both scan warpgroups drain EVERY accumulator, half the columns each, straight into registers (2 x tcgen05.ld.x64 per
 // thread) and release it as soon as the loads have landed: the accumulator is busy for one TMEM read latency instead of
 // a whole reduction, so the next MMA chain into it starts while its scores are still being reduced from registers.
-template <int MK, bool DEBUG>
+template <int MK, int TC_D, bool DEBUG>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_constant__ CUtensorMap xmap, const TcParams p) {
+    using C = Cfg<TC_D>;
+    constexpr int TC_G = C::G, KC = C::KC, NCH = C::NCH;
+    constexpr uint32_t BP_SBO = C::BP_SBO, BP_BYTES = C::BP_BYTES, CB_BYTES = C::CB_BYTES, MG_BYTES = C::MG_BYTES;
+    constexpr uint32_t PREP_BYTES = C::PREP_BYTES;
+    constexpr uint32_t OFF_RAW = C::OFF_RAW, OFF_AT = C::OFF_AT, OFF_BP = C::OFF_BP, OFF_CB = C::OFF_CB, OFF_AUX = C::OFF_AUX;
+    constexpr uint32_t OFF_RINV = C::OFF_RINV, OFF_ONES = C::OFF_ONES, OFF_MG = C::OFF_MG, OFF_RES = C::OFF_RES;
+    constexpr uint32_t OFF_SINFO = C::OFF_SINFO, OFF_BAR = C::OFF_BAR;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
@@ -475,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     mbar_wait<256>(RAW_EMPTY(st), ph ^ 1);
                     mbar_expect_tx(RAW_FULL(st), RAW_BYTES);
                     const int tile = part + it * p.parts;
-                    tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));
+                    tma_load_2d(sbase + OFF_RAW + st * RAW_BYTES, &xmap, s0 * TC_D, tile * TC_ROWS, RAW_FULL(st));   // 32 columns from the group's first
                 }
             }
         } else if (wq == 1) {
@@ -499,16 +521,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     const int acc = u & 1, cph = (u >> 1) & 1;
                     mbar_wait<32>(ACC_EMPTY(acc), cph ^ 1);
                     tc_fence_after();
-                    const uint64_t xhi = raw_desc0 + (uint64_t)((st * RAW_BYTES + i * 32) >> 4);
-                    const uint64_t xlo = at_desc0 + (uint64_t)((at * RAW_BYTES + i * 32) >> 4);
+                    // K = 8 step j of the sub-vector: 32 bytes further along the 128-byte row (A), two 16-byte chunks
+                    // further in the B image
+                    const uint64_t xhi = raw_desc0 + (uint64_t)((st * RAW_BYTES + i * (TC_D * 4)) >> 4);
+                    const uint64_t xlo = at_desc0 + (uint64_t)((at * RAW_BYTES + i * (TC_D * 4)) >> 4);
                     const uint64_t bhi = b_desc0 + (uint64_t)((i * BP_BYTES) >> 4);
                     const uint32_t d = tmem_base + acc * TC_N;
                     if (elect_one()) {
                         if (DEBUG && p.dbg_ts && blockIdx.x == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 0] = clock64();
-                        umma_tf32(d, xhi, bhi, idesc, 0);                                   // x_hi . c_hi
-                        umma_tf32(d, xhi, bhi + (256 >> 4), idesc, 1);                      // x_hi . c_lo
-                        if (use_norm) umma_tf32(d, ones_desc, bhi + (512 >> 4), idesc, 1);  // + ||c||^2
-                        umma_tf32(d, xlo, bhi, idesc, 1);                                   // x_lo . c_hi
+#pragma unroll
+                        for (int j = 0; j < KC; ++j) umma_tf32(d, xhi + 2 * j, bhi + 16 * j, idesc, j > 0);          // x_hi . c_hi
+#pragma unroll
+                        for (int j = 0; j < KC; ++j) umma_tf32(d, xhi + 2 * j, bhi + 8 * NCH + 16 * j, idesc, 1);    // x_hi . c_lo
+                        if (use_norm) umma_tf32(d, ones_desc, bhi + 16 * NCH, idesc, 1);                             // + ||c||^2
+#pragma unroll
+                        for (int j = 0; j < KC; ++j) umma_tf32(d, xlo + 2 * j, bhi + 16 * j, idesc, 1);              // x_lo . c_hi
                         umma_commit(ACC_FULL(acc));
                         if (i == last_act) { umma_commit(AT_EMPTY(at)); umma_commit(RAW_EMPTY(st)); }
                         if (DEBUG && p.dbg_ts && blockIdx.x == 0 && (int)u < p.dbg_ts_units) p.dbg_ts[u * 8 + 1] = clock64();
@@ -620,9 +647,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
         const int par = role - ROLE_HELP0;
         const int r = wq * 32 + lane;               // tile row
         const uint32_t r7 = (uint32_t)(r & 7);
-        // lane-rotated candidate order: the eight lanes of a quarter-warp read eight different 16-byte
-        // slots of their (arbitrary) 128-byte candidate groups -> conflict-free LDS.128 gathers
-        const int h0 = lane & 1, rot = (lane >> 1) & 3;
+        // lane-rotated gather order: lane-dependent rotations of the 16-byte chunk inside a candidate (rc) and of the
+        // candidate inside its group of four (rot) make the eight lanes of a quarter-warp read eight different 16-byte
+        // bank slots of their (arbitrary) candidate groups -> conflict-free LDS.128 gathers (D = 24: two-way at worst)
+        constexpr int RCB = (NCH == 2) ? 1 : (NCH == 8 ? 3 : 2);       // lane bits that rotate the chunk
+        const int rc = (lane & ((1 << RCB) - 1)) % NCH, rot = (lane >> RCB) & 3;
         const bool padded = p.k < TC_N;
 
         // x_lo tile + margins of row tile `ts` (runs one tile ahead of the MMAs)
@@ -649,10 +678,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
             float2 hm[TC_G];
 #pragma unroll
             for (int i = 0; i < TC_G; ++i) {
-                const float4 v0 = v[2 * i], v1 = v[2 * i + 1];
                 float nx2 = 0.f;
-                nx2 = fmaf(v0.x, v0.x, nx2); nx2 = fmaf(v0.y, v0.y, nx2); nx2 = fmaf(v0.z, v0.z, nx2); nx2 = fmaf(v0.w, v0.w, nx2);
-                nx2 = fmaf(v1.x, v1.x, nx2); nx2 = fmaf(v1.y, v1.y, nx2); nx2 = fmaf(v1.z, v1.z, nx2); nx2 = fmaf(v1.w, v1.w, nx2);
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    const float4 vq = v[NCH * i + q];
+                    nx2 = fmaf(vq.x, vq.x, nx2); nx2 = fmaf(vq.y, vq.y, nx2); nx2 = fmaf(vq.z, vq.z, nx2); nx2 = fmaf(vq.w, vq.w, nx2);
+                }
                 const float2 si = reinterpret_cast<const float2*>(sm + OFF_SINFO)[i];
                 float S;
                 if (MK == MK_COSINE) S = sqrt_approx(nx2) * 1.0000005f;
@@ -688,9 +719,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 ++u;
                 if (!raw_seen) { mbar_wait<128>(RAW_FULL(st), ph); raw_seen = true; }
                 const int s = s0 + i;
-                // this row's sub-vector, halves in this lane's gather order
-                const float4 xa = *reinterpret_cast<const float4*>(rawrow + (((2 * i + h0) ^ r7) << 4));
-                const float4 xb = *reinterpret_cast<const float4*>(rawrow + (((2 * i + (h0 ^ 1)) ^ r7) << 4));
+                // this row's sub-vector, its 16-byte chunks in this lane's gather order: xr[q] = chunk (q + rc) mod NCH
+                float4 xr[NCH];
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    int ch = q + rc; if (ch >= NCH) ch -= NCH;
+                    xr[q] = *reinterpret_cast<const float4*>(rawrow + (((NCH * i + ch) ^ r7) << 4));
+                }
                 mbar_wait<64>(RES_FULL(rs), rph);
                 const float2 rv = reinterpret_cast<const float2*>(sm + OFF_RES + rs * RES_BYTES)[r];
                 warp_arrive(RES_EMPTY(rs));
@@ -706,17 +741,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     // fp32 re-score of the four candidates in the tensor core's own form: -x.c/||c|| or ||c||^2 - 2 x.c
                     const int t = (int)(word & 63u);
                     const float M = __uint_as_float(word & ~63u);
-                    const uint8_t* gbase = reinterpret_cast<const uint8_t*>(cb) + t * 128;
+                    const uint8_t* gbase = reinterpret_cast<const uint8_t*>(cb) + t * (4 * TC_D * 4);
                     const float* rsc = reinterpret_cast<const float*>(sm + OFF_RINV + i * RINV_BYTES) + 4 * t;
                     float sc[4];
 #pragma unroll
                     for (int ii = 0; ii < 4; ++ii) {
                         const int q = (ii + rot) & 3;
-                        const float4 ca = *reinterpret_cast<const float4*>(gbase + q * 32 + h0 * 16);
-                        const float4 cc = *reinterpret_cast<const float4*>(gbase + q * 32 + (h0 ^ 1) * 16);
-                        float dot = ca.x * xa.x;
-                        dot = fmaf(ca.y, xa.y, dot); dot = fmaf(ca.z, xa.z, dot); dot = fmaf(ca.w, xa.w, dot);
-                        dot = fmaf(cc.x, xb.x, dot); dot = fmaf(cc.y, xb.y, dot); dot = fmaf(cc.z, xb.z, dot); dot = fmaf(cc.w, xb.w, dot);
+                        float dot = 0.f;
+#pragma unroll
+                        for (int qq = 0; qq < NCH; ++qq) {
+                            int ch = qq + rc; if (ch >= NCH) ch -= NCH;
+                            const float4 cv = *reinterpret_cast<const float4*>(gbase + q * (TC_D * 4) + ch * 16);
+                            dot = (qq == 0) ? cv.x * xr[0].x : fmaf(cv.x, xr[qq].x, dot);
+                            dot = fmaf(cv.y, xr[qq].y, dot); dot = fmaf(cv.z, xr[qq].z, dot); dot = fmaf(cv.w, xr[qq].w, dot);
+                        }
                         sc[ii] = (MK == MK_COSINE) ? dot * rsc[q] : fmaf(dot, -2.0f, rsc[q]);
                         if (padded && 4 * t + q >= p.k) sc[ii] = __int_as_float(0x7f800000);  // padding slot
                     }
@@ -734,13 +772,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 uint32_t todo = __ballot_sync(0xFFFFFFFFu, amb && live);
                 if (DEBUG && p.dbg_stats && lane == 0 && todo) atomicAdd(p.dbg_stats, (unsigned long long)__popc(todo));
                 if (todo) {
-                    ExactEval<MK> ev;  // this row's sub-vector in natural order
-                    ev.x.v[0] = h0 ? xb.x : xa.x; ev.x.v[1] = h0 ? xb.y : xa.y; ev.x.v[2] = h0 ? xb.z : xa.z; ev.x.v[3] = h0 ? xb.w : xa.w;
-                    ev.x.v[4] = h0 ? xa.x : xb.x; ev.x.v[5] = h0 ? xa.y : xb.y; ev.x.v[6] = h0 ? xa.z : xb.z; ev.x.v[7] = h0 ? xa.w : xb.w;
+                    ExactEval<MK, TC_D> ev;  // this row's sub-vector in natural order (re-read: the rotation is per lane)
+#pragma unroll
+                    for (int q = 0; q < NCH; ++q) {
+                        const float4 vq = *reinterpret_cast<const float4*>(rawrow + (((NCH * i + q) ^ r7) << 4));
+                        ev.x.v[4 * q] = vq.x; ev.x.v[4 * q + 1] = vq.y; ev.x.v[4 * q + 2] = vq.z; ev.x.v[4 * q + 3] = vq.w;
+                    }
                     while (todo) {
                         const int L = __ffs(todo) - 1;
                         todo &= todo - 1;
-                        ExactEval<MK> eo;
+                        ExactEval<MK, TC_D> eo;
 #pragma unroll
                         for (int q = 0; q < TC_D; ++q) eo.x.v[q] = __shfl_sync(0xFFFFFFFFu, ev.x.v[q], L);
                         eo.init();
@@ -767,11 +808,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                     if (p.codes) store_code(p.codes, p.code_bytes, (size_t)row * p.stride_row + (size_t)s * p.stride_sub, best);
                     if (p.recon) {  // pq.rs:193-195: f16::from_f32 of the chosen centroid
                         const float4* c = reinterpret_cast<const float4*>(cb + best * TC_D);
-                        const float4 c0 = c[0], c1 = c[1];
-                        __half2 h[4];
-                        h[0] = __floats2half2_rn(c0.x, c0.y); h[1] = __floats2half2_rn(c0.z, c0.w);
-                        h[2] = __floats2half2_rn(c1.x, c1.y); h[3] = __floats2half2_rn(c1.z, c1.w);
-                        *reinterpret_cast<uint4*>(p.recon + (size_t)row * p.dim + (size_t)s * TC_D) = *reinterpret_cast<uint4*>(h);
+                        __half* dst = p.recon + (size_t)row * p.dim + (size_t)s * TC_D;
+#pragma unroll
+                        for (int q = 0; q < NCH; q += 2) {
+                            const float4 c0 = c[q], c1 = c[q + 1];
+                            __half2 h[4];
+                            h[0] = __floats2half2_rn(c0.x, c0.y); h[1] = __floats2half2_rn(c0.z, c0.w);
+                            h[2] = __floats2half2_rn(c1.x, c1.y); h[3] = __floats2half2_rn(c1.z, c1.w);
+                            *reinterpret_cast<uint4*>(dst + 4 * q) = *reinterpret_cast<uint4*>(h);
+                        }
                     }
                 }
                 warp_arrive(RAW_EMPTY(st));
@@ -805,14 +850,25 @@ PFN_encodeTiled get_encode_fn() {
 // timing variant selected by vqb_debug_tc_variant: the warpgroup -> role map (see vqb_tc_assign_launch)
 int g_tc_variant = 1;
 
-template <int MK, bool DEBUG = false>
+template <int MK, int D, bool DEBUG = false>
 int launch_tc(vqb_ctx* ctx, const CUtensorMap& map, const TcParams& p, int grid) {
-    auto kern = k_tc_assign<MK, DEBUG>;
-    VQB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    kern<<<grid, TC_THREADS, SMEM_BYTES, ctx->stream>>>(map, p);
+    auto kern = k_tc_assign<MK, D, DEBUG>;
+    VQB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<D>::SMEM_BYTES));
+    kern<<<grid, TC_THREADS, Cfg<D>::SMEM_BYTES, ctx->stream>>>(map, p);
     VQB_LAUNCHED(ctx);
     return VQB_SUCCESS;
 }
+template <int MK>
+int launch_tc_d(vqb_ctx* ctx, const CUtensorMap& map, const TcParams& p, int grid, int d) {
+    switch (d) {
+        case 8: return launch_tc<MK, 8>(ctx, map, p, grid);
+        case 16: return launch_tc<MK, 16>(ctx, map, p, grid);
+        case 24: return launch_tc<MK, 24>(ctx, map, p, grid);
+        case 32: return launch_tc<MK, 32>(ctx, map, p, grid);
+    }
+    return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "sub_dim %d has no tensor-core path", d);
+}
+inline int tc_group(int d) { return d == 24 ? 1 : 32 / d; }   // Cfg<D>::G
 
 }  // namespace
 
@@ -832,22 +888,36 @@ int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUt
     return VQB_SUCCESS;
 }
 
-size_t vqb_tc_prep_bytes(size_t m) { return m * (size_t)PREP_BYTES + m * sizeof(SubInfo) + 256; }
+size_t vqb_tc_prep_bytes(size_t m, size_t d) {
+    if (d != 8 && d != 16 && d != 24 && d != 32) d = 8;
+    return m * prep_bytes_of(d) + m * sizeof(SubInfo) + 256;
+}
 
 bool vqb_tc_supported(int mk, const float* x, size_t n, size_t dim, size_t m, size_t k, size_t d) {
     (void)m;
     if (mk == MK_MANHATTAN || mk == MK_CHEBYSHEV) return false;   // not contractions: CUDA-core kernels by design
-    if (d != TC_D || k == 0 || k > TC_N) return false;
+    if ((d != 8 && d != 16 && d != 24 && d != 32) || k == 0 || k > TC_N) return false;
     if (dim % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return false;  // TMA: 16-byte aligned rows
     if (n == 0 || n >= (size_t)1 << 31) return false;
     return get_encode_fn() != nullptr;
 }
 
-int vqb_tc_prepare(vqb_ctx* ctx, int mk, const float* codebooks, size_t m, size_t k, void* prep, const uint32_t* go) {
+int vqb_tc_prepare(vqb_ctx* ctx, int mk, const float* codebooks, size_t m, size_t k, size_t d, void* prep, const uint32_t* go) {
     uint8_t* img = static_cast<uint8_t*>(prep);
-    SubInfo* sinfo = reinterpret_cast<SubInfo*>(img + ((m * (size_t)PREP_BYTES + 255) & ~(size_t)255));
-    if (mk == MK_COSINE) k_tc_prepare<MK_COSINE><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo, go);
-    else k_tc_prepare<MK_TRAIN><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo, go);
+    SubInfo* sinfo = reinterpret_cast<SubInfo*>(img + ((m * prep_bytes_of(d) + 255) & ~(size_t)255));
+#define VQB_PREP_CASE(DD)                                                                                                  \
+    case DD:                                                                                                               \
+        if (mk == MK_COSINE) k_tc_prepare<MK_COSINE, DD><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo, go); \
+        else k_tc_prepare<MK_TRAIN, DD><<<(unsigned)m, TC_N, 0, ctx->stream>>>(codebooks, (int)k, img, sinfo, go);          \
+        break;
+    switch (d) {
+        VQB_PREP_CASE(8)
+        VQB_PREP_CASE(16)
+        VQB_PREP_CASE(24)
+        VQB_PREP_CASE(32)
+        default: return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "sub_dim %zu has no tensor-core path", d);
+    }
+#undef VQB_PREP_CASE
     VQB_LAUNCHED(ctx);
     return VQB_SUCCESS;
 }
@@ -863,12 +933,13 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
     p.go = go;
     const uint8_t* img = static_cast<const uint8_t*>(prep);
     p.prep = img;
-    p.sinfo = reinterpret_cast<const SubInfo*>(img + ((m * (size_t)PREP_BYTES + 255) & ~(size_t)255));
+    const int d = (int)(dim / m);
+    p.sinfo = reinterpret_cast<const SubInfo*>(img + ((m * prep_bytes_of((size_t)d) + 255) & ~(size_t)255));
     p.active = active_dev;
     p.codes = codes; p.recon = recon;
     p.n = n; p.stride_row = stride_row; p.stride_sub = stride_sub;
     p.dim = (int)dim; p.m = (int)m; p.k = (int)k;
-    p.n_groups = (int)((m + TC_G - 1) / TC_G);
+    p.n_groups = (int)((m + tc_group(d) - 1) / tc_group(d));
     p.num_tiles = (int)((n + TC_ROWS - 1) / TC_ROWS);
     p.parts = std::max(1, std::min(p.num_tiles, ctx->sm_count / p.n_groups));
     p.code_bytes = code_bytes;
@@ -883,15 +954,16 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
     p.role_map = role_maps[g_tc_variant & 3];
     const int grid = p.n_groups * p.parts;
     if (dbg_scores || dbg_stats || dbg_ts) {
-        if (mk == MK_COSINE) return launch_tc<MK_COSINE, true>(ctx, map, p, grid);
-        if (mk == MK_TRAIN) return launch_tc<MK_TRAIN, true>(ctx, map, p, grid);
+        if (d != 8 && (dbg_ts || d != 16)) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for sub_dim 8 (and scores for 16) only");
+        if (mk == MK_COSINE) return d == 8 ? launch_tc<MK_COSINE, 8, true>(ctx, map, p, grid) : launch_tc<MK_COSINE, 16, true>(ctx, map, p, grid);
+        if (mk == MK_TRAIN) return d == 8 ? launch_tc<MK_TRAIN, 8, true>(ctx, map, p, grid) : launch_tc<MK_TRAIN, 16, true>(ctx, map, p, grid);
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for the training and cosine kinds only");
     }
     switch (mk) {
-        case MK_SQEUCLID: return launch_tc<MK_SQEUCLID>(ctx, map, p, grid);
-        case MK_EUCLID: return launch_tc<MK_EUCLID>(ctx, map, p, grid);
-        case MK_COSINE: return launch_tc<MK_COSINE>(ctx, map, p, grid);
-        case MK_TRAIN: return launch_tc<MK_TRAIN>(ctx, map, p, grid);
+        case MK_SQEUCLID: return launch_tc_d<MK_SQEUCLID>(ctx, map, p, grid, d);
+        case MK_EUCLID: return launch_tc_d<MK_EUCLID>(ctx, map, p, grid, d);
+        case MK_COSINE: return launch_tc_d<MK_COSINE>(ctx, map, p, grid, d);
+        case MK_TRAIN: return launch_tc_d<MK_TRAIN>(ctx, map, p, grid, d);
     }
     return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "metric kind %d has no tensor-core path", mk);
 }
@@ -921,10 +993,10 @@ extern "C" int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, siz
     if (!vqb_tc_supported(mk, static_cast<const float*>(xin.dev), n, dim, m, k, d))
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "shape not covered by the tensor-core kernel");
     DevBuf prep, stats;
-    VQB_CUDA(ctx, prep.alloc(vqb_tc_prep_bytes(m)));
+    VQB_CUDA(ctx, prep.alloc(vqb_tc_prep_bytes(m, d)));
     VQB_CUDA(ctx, stats.alloc(8));
     VQB_CUDA(ctx, cudaMemsetAsync(stats.p, 0, 8, ctx->stream));
-    VQB_TRY(vqb_tc_prepare(ctx, mk, static_cast<const float*>(cin.dev), m, k, prep.p));
+    VQB_TRY(vqb_tc_prepare(ctx, mk, static_cast<const float*>(cin.dev), m, k, d, prep.p));
     VQB_TRY(vqb_tc_assign_launch(ctx, mk, static_cast<const float*>(xin.dev), n, dim, m, k, prep.p, nullptr, co.dev, 4,
                                  /*stride_row=*/1, /*stride_sub=*/n, nullptr, static_cast<float*>(so.dev),
                                  stats.as<unsigned long long>(), sub));
@@ -951,11 +1023,11 @@ extern "C" int vqb_debug_tc_timeline(vqb_ctx* ctx, const float* x, size_t n, siz
     if (!vqb_tc_supported(MK_COSINE, static_cast<const float*>(xin.dev), n, dim, m, k, d))
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "shape not covered by the tensor-core kernel");
     DevBuf prep, ts, codes;
-    VQB_CUDA(ctx, prep.alloc(vqb_tc_prep_bytes(m)));
+    VQB_CUDA(ctx, prep.alloc(vqb_tc_prep_bytes(m, d)));
     VQB_CUDA(ctx, ts.alloc((size_t)units * 8 * 8));
     VQB_CUDA(ctx, codes.alloc(n * m));
     VQB_CUDA(ctx, cudaMemsetAsync(ts.p, 0, (size_t)units * 64, ctx->stream));
-    VQB_TRY(vqb_tc_prepare(ctx, MK_COSINE, static_cast<const float*>(cin.dev), m, k, prep.p));
+    VQB_TRY(vqb_tc_prepare(ctx, MK_COSINE, static_cast<const float*>(cin.dev), m, k, d, prep.p));
     VQB_TRY(vqb_tc_assign_launch(ctx, MK_COSINE, static_cast<const float*>(xin.dev), n, dim, m, k, prep.p, nullptr, codes.p, 1,
                                  m, 1, nullptr, nullptr, nullptr, 0, ts.as<unsigned long long>(), units));
     VQB_CUDA(ctx, cudaMemcpyAsync(ts_out, ts.p, (size_t)units * 64, cudaMemcpyDeviceToHost, ctx->stream));

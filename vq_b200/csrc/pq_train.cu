@@ -674,7 +674,7 @@ struct TrainWs {
         g_subs = b.take<int>(gcap);
         g_dst = b.take<long long>(gcap);
         g_vals = b.take<float>(gcap * d);
-        tc_prep = b.take<uint8_t>(vqb_tc_prep_bytes(m));
+        tc_prep = b.take<uint8_t>(vqb_tc_prep_bytes(m, d));
     }
     // Picks the update kernels for this shape and carves the arrays out of the context's grow-only slab.
     int setup(vqb_ctx* ctx, const float* x, size_t n_, size_t dim_, size_t m_, size_t k_, uint32_t update_mode,
@@ -743,7 +743,7 @@ int assign_train(vqb_ctx* ctx, const TrainArgs& a, TrainWs& ws, void* codes, uin
         return vqb_fail(ctx, VQB_ERR_INVALID_INPUT,
                         "tensor-core assignment needs sub_dim 8, k <= 256 and 16-byte aligned rows");
     if (tc_ok && (a.assign_mode == VQB_ASSIGN_TENSOR || (a.assign_mode == VQB_ASSIGN_AUTO && a.n >= VQB_TC_MIN_ROWS))) {
-        VQB_TRY(vqb_tc_prepare(ctx, MK_TRAIN, ws.cb, a.m, a.k, ws.tc_prep, go));
+        VQB_TRY(vqb_tc_prepare(ctx, MK_TRAIN, ws.cb, a.m, a.k, a.d, ws.tc_prep, go));
         return vqb_tc_assign_launch(ctx, MK_TRAIN, a.x, a.n, a.dim, a.m, a.k, ws.tc_prep, ws.is_active, codes, code_bytes,
                                     /*stride_row=*/1, /*stride_sub=*/a.n, nullptr, nullptr, nullptr, 0, nullptr, 0, go);
     }
