@@ -59,15 +59,19 @@ def debug_scores(eng, x, cb, sub, cosine):
     return scores, int(rescans[0]), codes
 
 
+@pytest.mark.parametrize("sub_dim", [8, 16, 24, 32])
 @pytest.mark.parametrize("scale", [1.0, 1e-3, 1e4])
-def test_tensor_scores_within_margin(eng, scale):
+def test_tensor_scores_within_margin(eng, scale, sub_dim):
     """|tcgen05 score - float64 score| must stay far inside the margin M = KAPPA * S used to prune.
 
     Budget: pruning is sound while 2 * (err_tensor + err_reference) <= KAPPA * S.  The
     reference's own rounding is <= 8e-7 * S (cosine, worst case), the tensor path's rigorous bound is
     1.2e-6 * S (x_lo truncated by the tensor core, dropped x_lo.c_lo, c_lo rounding); KAPPA / 8 = 9.5e-7
-    is the measured-error guard that keeps the sum under KAPPA / 2 with room to spare."""
-    n, dim, m, k = 20_000, 64, 8, 256
+    is the measured-error guard that keeps the sum under KAPPA / 2 with room to spare.  The margin of sub_dim D is
+    KAPPA * D / 8 (more MMAs and products per score, longer sums in the reference)."""
+    KAPPA = 2.0 ** -17 * (sub_dim // 8)
+    n, m, k = 20_000, 8, 256
+    dim = m * sub_dim
     x = mixture(n, dim, 5, scale=scale)
     cb = sample_codebooks(x, m, k, 6)
     for sub in (0, 5):

@@ -120,7 +120,9 @@ struct SubInfo {        // per subspace, written by the prepare kernel
 // core (<= 2^-21 |x_i|), c = c_hi + c_lo + (<= 2^-23 |c_i|), dropped x_lo.c_lo (<= 2^-21), fp32
 // accumulation of <= 32 products, the norm pieces, and the reference's own rounding (<= 11 ulp of d).
 // Measured on B200 (tests/test_gpu_tensor.py::test_tensor_scores_within_margin).
-constexpr float KAPPA = 1.0f / 131072.0f;  // 2^-17 = 7.6e-6
+// Longer sub-vectors chain more MMAs and more products per score (and the reference's own sums are longer): the margin
+// grows in proportion, KAPPA * (D / 8); tests/test_gpu_tensor.py measures the score error for every D against it.
+constexpr float KAPPA = 1.0f / 131072.0f;  // 2^-17 = 7.6e-6 at sub_dim 8
 
 // ------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -694,7 +696,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 if (MK == MK_COSINE) amb = amb || !(nx2 > 4.0f * FLT_MIN);
                 const uint32_t sexp = (__float_as_uint(S) >> 23) & 0xFFu;
                 hm[i].x = amb ? 1.0f : __uint_as_float((294u - sexp) << 23);
-                hm[i].y = amb ? -1.0f : KAPPA * S;
+                hm[i].y = amb ? -1.0f : (KAPPA * (float)(TC_D / 8)) * S;
             }
             mbar_wait<128>(MG_EMPTY(mg), mph ^ 1);
 #pragma unroll
@@ -954,10 +956,15 @@ int vqb_tc_assign_launch(vqb_ctx* ctx, int mk, const float* x, size_t n, size_t 
     p.role_map = role_maps[g_tc_variant & 3];
     const int grid = p.n_groups * p.parts;
     if (dbg_scores || dbg_stats || dbg_ts) {
-        if (d != 8 && (dbg_ts || d != 16)) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for sub_dim 8 (and scores for 16) only");
-        if (mk == MK_COSINE) return d == 8 ? launch_tc<MK_COSINE, 8, true>(ctx, map, p, grid) : launch_tc<MK_COSINE, 16, true>(ctx, map, p, grid);
-        if (mk == MK_TRAIN) return d == 8 ? launch_tc<MK_TRAIN, 8, true>(ctx, map, p, grid) : launch_tc<MK_TRAIN, 16, true>(ctx, map, p, grid);
-        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for the training and cosine kinds only");
+        if (mk != MK_COSINE && mk != MK_TRAIN)
+            return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "debug capture exists for the training and cosine kinds only");
+        switch (d) {
+            case 8: return mk == MK_COSINE ? launch_tc<MK_COSINE, 8, true>(ctx, map, p, grid) : launch_tc<MK_TRAIN, 8, true>(ctx, map, p, grid);
+            case 16: return mk == MK_COSINE ? launch_tc<MK_COSINE, 16, true>(ctx, map, p, grid) : launch_tc<MK_TRAIN, 16, true>(ctx, map, p, grid);
+            case 24: return mk == MK_COSINE ? launch_tc<MK_COSINE, 24, true>(ctx, map, p, grid) : launch_tc<MK_TRAIN, 24, true>(ctx, map, p, grid);
+            case 32: return mk == MK_COSINE ? launch_tc<MK_COSINE, 32, true>(ctx, map, p, grid) : launch_tc<MK_TRAIN, 32, true>(ctx, map, p, grid);
+        }
+        return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "sub_dim %d has no tensor-core path", d);
     }
     switch (mk) {
         case MK_SQEUCLID: return launch_tc_d<MK_SQEUCLID>(ctx, map, p, grid, d);
