@@ -16,7 +16,7 @@ for _ in range(2):
     eng.check(eng.lib.vqb_debug_tc_timeline(eng.h, x.data_ptr(), n, dim, m, k, cb.data_ptr(), ts.ctypes.data, units))
 t = ts.astype(np.int64)
 t0 = t[t > 0].min()
-names = ["iss_saw_empty", "iss_issued", "scan_saw_full", "scan_released", "scan_published", "res_saw", "res_done", "split_pub"]
+names = ["iss_saw_empty", "iss_issued", "scan_saw_full", "scan_released", "scan_published", "res_saw", "res_done", "released_last"]
 lo, hi = 200, 216
 print("unit " + " ".join(f"{nm:>14s}" for nm in names))
 for u in range(lo, hi):
@@ -27,4 +27,6 @@ print("median cycles: unit period (issuer)", np.median(np.diff(t[100:380, 0])),
       "| post (released -> published)", d(4, 3), "| published -> resolve saw", d(5, 4), "| resolve dur", d(6, 5))
 # accumulator a is released by unit u and next observed empty by unit u+2's issue
 rel = t[100:378, 3]; nxt = t[102:380, 0]
-print("median released(u) -> issuer saw empty(u+2):", np.median(nxt - rel), "| split_pub(u) - iss_saw_empty(u):", d(7, 0))
+rl = t[100:378, 7]
+print("median released by warp 0 (u) -> issuer saw empty(u+2):", np.median(nxt - rel), "| last warp's release after warp 0's:", d(7, 3),
+      "| last release(u) -> issuer saw empty(u+2):", np.median(nxt - rl))

@@ -599,6 +599,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 tc_fence_before();
                 warp_arrive(ACC_EMPTY(acc));  // TMEM accumulator may be overwritten by the next MMA chain
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 3] = clock64();
+                if (DEBUG && p.dbg_ts && blockIdx.x == 0 && lane == 0 && (int)(u - 1) < p.dbg_ts_units)   // last warp's release
+                    atomicMax(&p.dbg_ts[(u - 1) * 8 + 7], (unsigned long long)clock64());
 
                 // ---- row minimum
                 float t1[22];
@@ -674,7 +676,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 *reinterpret_cast<float4*>(atrow + ((c ^ r7) << 4)) = make_float4(tf32_lo(v[c].x), tf32_lo(v[c].y), tf32_lo(v[c].z), tf32_lo(v[c].w));
             fence_proxy_async();
             warp_arrive(AT_FULL(at));
-            if (DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && ts * n_act < p.dbg_ts_units) p.dbg_ts[ts * n_act * 8 + 7] = clock64();
             // every subspace's error margin M = KAPPA * S and indicator scale H = 2^(40 - floor(log2 S)):
             // (th - g) * H >= 1 for every representable g < th in the score range, th * H far from overflow
             float2 hm[TC_G];
@@ -1016,7 +1017,7 @@ extern "C" int vqb_debug_tc_scores(vqb_ctx* ctx, int cosine, const float* x, siz
 
 // Diagnostics: SM-clock stamps of CTA 0's per-unit hand-offs in one cosine-encode pass (ts_out[units][8], host):
 // 0 issuer saw ACC_EMPTY, 1 issuer issued + committed, 2 scan saw ACC_FULL, 3 scan released the accumulator,
-// 4 scan published its result, 5 resolve saw it, 6 resolve done, 7 splitter published x_lo.
+// 4 scan published its result, 5 resolve saw it, 6 resolve done, 7 the last scan warp released the accumulator.
 extern "C" int vqb_debug_tc_timeline(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t m, size_t k,
                                      const float* codebooks, uint64_t* ts_out, int units) {
     if (!ctx || !x || !codebooks || !ts_out) return VQB_ERR_NULL_PTR;
