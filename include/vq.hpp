@@ -23,6 +23,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <array>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -79,9 +80,29 @@ public:
         if (!e) e = std::make_shared<Engine>(device);
         return e;
     }
+    // ---- multi-GPU: one process and one Engine per GPU; the library owns the NCCL communicator.  Rank 0
+    // draws an id and ships its VQB_COMM_ID_BYTES to the other ranks by any means (MPI, a file, a socket); every rank
+    // then calls comm_init (collective).  Training with a RowShard issues one ncclAllReduce per iteration.
+    static std::array<uint8_t, VQB_COMM_ID_BYTES> comm_unique_id() {
+        std::array<uint8_t, VQB_COMM_ID_BYTES> id{};
+        if (vqb_comm_unique_id(id.data()) != VQB_SUCCESS) throw VqError::ffi("vqb_comm_unique_id failed (is libnccl.so.2 loadable?)");
+        return id;
+    }
+    void comm_init(const std::array<uint8_t, VQB_COMM_ID_BYTES>& id, int rank, int world) { check(vqb_comm_init_rank(ctx_, id.data(), rank, world)); }
+    void comm_destroy() { check(vqb_comm_destroy(ctx_)); }
+    std::pair<int, int> comm_info() const {  // {rank, world}; {0, 1} without a communicator
+        int r = 0, w = 1;
+        check(vqb_comm_info(ctx_, &r, &w));
+        return {r, w};
+    }
 private:
     vqb_ctx* ctx_ = nullptr;
 };
+
+// The rows this rank holds of a training set that is sharded over the ranks of the engine's communicator: rows
+// [row_offset, row_offset + n_local) of n_global.  Initial and re-seed indices are GLOBAL row numbers (the same stream on
+// every rank); the owner of a row contributes it through the per-iteration sum.
+struct RowShard { uint64_t row_offset = 0, n_global = 0; };
 
 inline std::string get_simd_backend() { return vqb_backend_name(); }  // src/core/hsdlib_ffi.rs:144-155
 
@@ -353,6 +374,13 @@ public:
         if (n == 0) throw VqError::empty_input();
         init(data, n, dim, m, k, max_iters, distance, seed, std::move(eng), indices);
     }
+    // Row-sharded form (no counterpart in the single-process crate): `data` holds this rank's n_local rows of
+    // shard.n_global; the engine must have a communicator (Engine::comm_init).  Every rank gets the same codebooks.
+    ProductQuantizer(const float* data, size_t n_local, size_t dim, size_t m, size_t k, size_t max_iters, Distance distance,
+                     uint64_t seed, const RowShard& shard, std::shared_ptr<Engine> eng, IndexSource* indices = nullptr) {
+        if (shard.n_global == 0) throw VqError::empty_input();
+        init(data, n_local, dim, m, k, max_iters, distance, seed, std::move(eng), indices, &shard);
+    }
     ~ProductQuantizer() { if (pq_) vqb_pq_destroy(pq_); }
     ProductQuantizer(const ProductQuantizer&) = delete;
     ProductQuantizer& operator=(const ProductQuantizer&) = delete;
@@ -388,8 +416,9 @@ private:
         auto* st = static_cast<ReseedState*>(user);
         return st->src->choose(s, st->n);
     }
-    void init(const float* data, size_t n, size_t dim, size_t m, size_t k, size_t max_iters, Distance distance, uint64_t seed,
-              std::shared_ptr<Engine> eng, IndexSource* indices) {
+    void init(const float* data, size_t n_local, size_t dim, size_t m, size_t k, size_t max_iters, Distance distance, uint64_t seed,
+              std::shared_ptr<Engine> eng, IndexSource* indices, const RowShard* shard = nullptr) {
+        const size_t n = shard ? (size_t)shard->n_global : n_local;   // the crate's checks and the index stream see the whole set
         if (m == 0) throw VqError::invalid_parameter("m", "must be greater than 0");  // the crate panics on dim % 0 (pq.rs:112)
         if (dim < m) throw VqError::invalid_parameter("m", "must be at most the data dimension (" + std::to_string(dim) + ")");  // pq.rs:106-111
         if (dim % m) throw VqError::invalid_parameter("m", "dimension (" + std::to_string(dim) + ") must be divisible by m");   // pq.rs:112-117
@@ -413,9 +442,10 @@ private:
         o.assign_mode = VQB_ASSIGN_AUTO;
         o.reseed = &ProductQuantizer::reseed_tramp;
         o.reseed_user = &st;
+        if (shard) { o.flags = VQB_TRAIN_USE_COMM; o.row_offset = shard->row_offset; o.n_global = shard->n_global; }
         cb_.assign(m * k * (dim / m), 0.f);
         iters_.assign(m, 0);
-        eng_->check(vqb_pq_train(eng_->ctx(), data, n, dim, m, k, max_iters, init_idx.data(), &o, cb_.data(), iters_.data()));
+        eng_->check(vqb_pq_train(eng_->ctx(), data, n_local, dim, m, k, max_iters, init_idx.data(), &o, cb_.data(), iters_.data()));
         eng_->check(vqb_pq_create(eng_->ctx(), cb_.data(), m, k, dim / m, (int)distance, &pq_));
     }
     size_t m_ = 0, k_ = 0, dim_ = 0;

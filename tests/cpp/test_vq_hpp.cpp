@@ -94,6 +94,18 @@ int main(int argc, char** argv) {
         std::printf("\ns");
         for (uint8_t c : sq.quantize(rows[0])) std::printf(" %u", c);
         std::printf("\nd %.9g\n", distance_compute(Distance::Manhattan, rows[0], rows[1]));
+        // library-owned communicator with one rank: the row-sharded constructor must give the same codebooks
+        {
+            auto eng = Engine::shared();
+            eng->comm_init(Engine::comm_unique_id(), 0, 1);
+            auto info = eng->comm_info();
+            std::vector<float> flat;
+            for (const auto& r : rows) flat.insert(flat.end(), r.begin(), r.end());
+            RowShard sh{0, rows.size()};
+            ProductQuantizer pqs(flat.data(), rows.size(), 16, 2, 16, 4, Distance::CosineDistance, 42, sh, eng);
+            std::printf("comm %d %d %d\n", info.first, info.second, pqs.codebooks() == pq.codebooks() ? 1 : 0);
+            eng->comm_destroy();
+        }
         return 0;
     }
     return 64;

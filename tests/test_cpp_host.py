@@ -82,3 +82,5 @@ def test_cpp_mirror_equals_python_mirror(driver):
     assert [int(v) for v in got["b"]] == vq.BinaryQuantizer(0.5, 0, 1).quantize(rows[0]).tolist()
     assert [int(v) for v in got["s"]] == vq.ScalarQuantizer(-1.0, 8.0, 256).quantize(rows[0]).tolist()
     assert F(float(got["d"][0])) == F(vq.Distance.manhattan().compute(rows[0], rows[1]))
+    # Engine::comm_init (library NCCL communicator, one rank) + the RowShard constructor: same codebooks
+    assert got["comm"] == ["0", "1", "1"]
