@@ -209,6 +209,29 @@ def test_train_step_teacher_forced(eng, oracle, dim, m, k, n):
         state = nxt
 
 
+@pytest.mark.parametrize("sub_dim", [4, 8, 12, 16, 20, 24, 32, 40, 64])
+@pytest.mark.parametrize("k,n", [(256, 9000), (16, 4100), (256, 5000)])
+def test_train_step_every_update_kernel_shape(eng, oracle, sub_dim, k, n):
+    """One teacher-forced iteration across the shapes that select different update / assignment kernels (tile kernels
+    for sub_dim 8 / 16 / 32 and n >= 4096, radix grouping otherwise; tensor assignment for sub_dim 8 / 16 / 24 / 32):
+    ORDERED means bit-identical with the oracle, FAST within 1e-4.  (sub_dim 32 with the ordered tile kernel once read a
+    swizzled tile as plain rows -- no test had that shape.)"""
+    m = 3 if sub_dim <= 32 else 2
+    dim = m * sub_dim
+    x = mixture(n, dim, 77 + sub_dim)
+    rng = np.random.default_rng(13)
+    state = np.stack([x[rng.choice(n, k, replace=False), s * sub_dim:(s + 1) * sub_dim] for s in range(m)]).astype(F)
+    got, changed, counts = gpu_train_step(eng, x, state)
+    fast, _, _ = gpu_train_step(eng, x, state, update="fast")
+    for s in range(m):
+        want, assign, ch, empt = oracle.lbg_step(x, s * sub_dim, sub_dim, state[s])
+        nonempty = np.ones(k, bool); nonempty[empt] = False
+        assert np.array_equal(counts[s], np.bincount(assign, minlength=k))
+        assert bool(changed[s]) == ch
+        assert np.array_equal(bits(got[s][nonempty]), bits(want[nonempty])), s
+        assert np.linalg.norm(fast[s] - want) / np.linalg.norm(want) <= 1e-4
+
+
 def test_pq_train_end_to_end_bit_exact(vq, oracle):
     """C1-shaped (reduced n): 128-d, m 8, k 256, 10 iterations, explicit index stream."""
     n, dim, m, k, iters = 20000, 128, 8, 256, 10

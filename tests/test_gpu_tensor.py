@@ -186,9 +186,10 @@ def test_tensor_mode_rejects_unsupported_shapes(vq):
     assert pq.encode(x).shape == (2000, 8)  # auto: CUDA-core kernel
 
 
-def test_tensor_training_end_to_end_matches_oracle(vq, oracle):
+@pytest.mark.parametrize("dim,m", [(64, 8), (128, 8), (96, 4), (64, 2)])   # sub_dim 8, 16, 24, 32
+def test_tensor_training_end_to_end_matches_oracle(vq, oracle, dim, m):
     """Ordered update + tensor assignment: the trained codebooks stay bit-identical with the oracle."""
-    n, dim, m, k, iters = 20_000, 64, 8, 256, 8
+    n, k, iters = 20_000, 256, 8
     x = mixture(n, dim, 20240)
     init, _ = vq.draw_init_indices(n, m, k, 42)
     pq = vq.ProductQuantizer(x, m, k, iters, vq.Distance.cosine(), init_idx=init, reseed=lambda s: 0, assign="tensor")

@@ -290,7 +290,9 @@ int vqb_tc_prepare(vqb_ctx* ctx, int metric_kind, const float* codebooks, size_t
 // the 2-D tensor map over a row-major f32 matrix x[n, dim] used by the TMA-fed kernels: box = box_cols floats x 128 rows
 // (32 columns: SWIZZLE_128B, one 128-byte line per row; otherwise unswizzled rows of box_cols floats)
 struct CUtensorMap_st;
-int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out, int box_cols = 32);
+// swizzle: -1 = by width (32 columns swizzled), 0 = plain rows, 1 = SWIZZLE_128B (32 columns only)
+int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out, int box_cols = 32,
+                         int swizzle = -1);
 int vqb_tc_assign_launch(vqb_ctx* ctx, int metric_kind, const float* x, size_t n, size_t dim, size_t m, size_t k,
                          const void* prep, const int* active_dev, void* codes, uint32_t code_bytes,
                          size_t code_stride_row, size_t code_stride_sub, __half* recon,

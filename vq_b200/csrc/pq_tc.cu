@@ -875,7 +875,7 @@ inline int tc_group(int d) { return d == 24 ? 1 : 32 / d; }   // Cfg<D>::G
 
 }  // namespace
 
-int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out, int box_cols) {
+int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUtensorMap_st* out, int box_cols, int swizzle) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled is not available");
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n};
@@ -885,7 +885,8 @@ int vqb_make_x_tensormap(vqb_ctx* ctx, const float* x, size_t n, size_t dim, CUt
     // 32 columns = one 128-byte line per row, swizzled (what the tensor core and the tile kernels expect); any other
     // width lands as plain rows of box_cols floats
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     (swizzle < 0 ? box_cols == 32 : swizzle != 0) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return vqb_fail(ctx, VQB_FAILURE, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return VQB_SUCCESS;

@@ -784,7 +784,7 @@ int train_iteration(vqb_ctx* ctx, TrainWs& ws, const TrainArgs& a, uint32_t* sta
         }
     } else if (ws.kind == UPD_ORDERED_TILES) {
         CUtensorMap map;
-        VQB_TRY(vqb_make_x_tensormap(ctx, a.x, n, a.dim, &map, (int)d));
+        VQB_TRY(vqb_make_x_tensormap(ctx, a.x, n, a.dim, &map, (int)d, /*swizzle=*/0));   // the kernel reads plain rows of d floats
         UoParams p;
         p.codes = static_cast<const uint8_t*>(ws.codes); p.n = n; p.m = (int)m; p.k = (int)k;
         p.sub_list = ws.sub_list; p.ctrl = ws.ctrl; p.partial = ws.partial; p.cnt_partial = ws.cnt_partial;
