@@ -330,6 +330,33 @@ def test_pq_encode_exact(vq, oracle, metric, dim, m, k):
     assert np.array_equal(bits(pq.decode(codes)), bits(want_recon.astype(F)))
 
 
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("sub_dim", [4, 8, 12, 16, 24, 32, 40])
+@pytest.mark.parametrize("k,n", [(7, 1030), (256, 1000), (256, 4100), (300, 4100)])
+def test_pq_encode_kernel_selection_sweep(vq, oracle, metric, sub_dim, k, n):
+    """Encode in AUTO mode across the shapes that select different assignment kernels (tensor kernel for sub_dim 8 / 16 /
+    24 / 32, k <= 256, n >= 1024; tiled Manhattan for sub_dim 8, n >= 4096; the CUDA-core kernel otherwise): codes and f16
+    reconstructions identical with the oracle, from host buffers and from device buffers."""
+    torch = pytest.importorskip("torch")
+    m = 3
+    dim = m * sub_dim
+    x = mixture(n, dim, 500 + sub_dim + k)
+    rng = np.random.default_rng(sub_dim * 1000 + k)
+    cb = np.stack([x[rng.choice(n, k, replace=False), s * sub_dim:(s + 1) * sub_dim] for s in range(m)]).astype(F)
+    cb[0, min(3, k - 1)] = cb[0, 1]
+    x[0] = 0.0
+    x[1, :sub_dim] = np.nan
+    pq = vq.ProductQuantizer.from_codebooks(cb, vq.Distance(metric))
+    want_codes, want_recon = oracle.pq_encode(cb, metric, x, sem="avx512")
+    codes, recon = pq.encode_with_recon(x)
+    assert np.array_equal(codes.astype(np.uint32), want_codes)
+    assert np.array_equal(bits(recon), bits(want_recon))
+    xd = torch.from_numpy(x).cuda()
+    codes_d, recon_d = pq.encode_with_recon(xd)
+    assert np.array_equal(codes_d.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, want_codes.astype(np.int64))
+    assert np.array_equal(recon_d.cpu().numpy().view(np.uint16), want_recon.view(np.uint16))
+
+
 def test_pq_encode_vs_real_hsdlib_near_tie_rule(vq, oracle):
     """Against hsdlib compiled verbatim from the reference, whatever this host dispatches to:
     >= 99.9 % agreement and every disagreement within 1e-5 relative distance."""
