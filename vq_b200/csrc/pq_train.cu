@@ -235,7 +235,8 @@ k_chain_sums(const float* __restrict__ x, size_t n, size_t row_stride, size_t su
 constexpr int UT_ROWS = 512, UT_THREADS = 1024, UT_RW = UT_ROWS / 32;
 constexpr uint32_t UT_TILE_BYTES = UT_ROWS * 128;
 constexpr uint32_t UT_OFF_MASK = 2 * UT_TILE_BYTES;                       // [4][16][256] u32
-constexpr uint32_t UT_OFF_BAR = UT_OFF_MASK + 4 * UT_RW * 256 * 4;
+constexpr uint32_t UT_OFF_NZ = UT_OFF_MASK + 4 * UT_RW * 256 * 4;         // [4][256] u32: which of a cluster's 16 mask words are non-empty
+constexpr uint32_t UT_OFF_BAR = UT_OFF_NZ + 4 * 256 * 4;
 constexpr uint32_t UT_SMEM = UT_OFF_BAR + 64 + 1024;
 static_assert(UT_SMEM <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 
@@ -268,9 +269,11 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_update_tiles(const __grid_con
         if (p.is_active[s0 + i]) act_mask |= 1u << i;
     if (act_mask == 0) return;
     uint32_t* mask = reinterpret_cast<uint32_t*>(sm + UT_OFF_MASK);
+    uint32_t* nzmap = reinterpret_cast<uint32_t*>(sm + UT_OFF_NZ);
     const uint32_t bar0 = sbase + UT_OFF_BAR;
     const int my_tiles = (p.num_tiles - part + p.parts - 1) / p.parts;
     for (int t = tid; t < G * UT_RW * 256 / 4; t += UT_THREADS) reinterpret_cast<uint4*>(mask)[t] = make_uint4(0, 0, 0, 0);
+    for (int t = tid; t < 4 * 256; t += UT_THREADS) nzmap[t] = 0;
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -318,7 +321,10 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_update_tiles(const __grid_con
         // ---- A: membership bits (the masks are all zero here)
 #pragma unroll
         for (int a = 0; a < 2; ++a)
-            if (cde[a] != 0xFFFFFFFFu) atomicOr(&mask[((sp + 2 * a) * UT_RW + rw) * 256 + cde[a]], bit);
+            if (cde[a] != 0xFFFFFFFFu) {
+                atomicOr(&mask[((sp + 2 * a) * UT_RW + rw) * 256 + cde[a]], bit);
+                atomicOr(&nzmap[(sp + 2 * a) * 256 + cde[a]], 1u << rw);
+            }
         __syncthreads();
         if (it + 1 < my_tiles) fetch_codes(it + 1, cde);         // in flight while this tile is summed
         // ---- B: the x tile has landed; add the members' chunks, lowest row first
@@ -333,18 +339,14 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_update_tiles(const __grid_con
             const uint8_t* xt = sm + st * UT_TILE_BYTES;
             // which of the 16 mask words of this cluster are non-empty (about two are), then only those are walked:
             // the warp iterates max-over-lanes(non-empty words) times instead of once per word
-            uint32_t nz = 0;
-#pragma unroll
-            for (int w = 0; w < UT_RW; ++w) {
-                const uint32_t m = mask[(sb * UT_RW + w) * 256 + j];
-                nz |= (m != 0u ? 1u : 0u) << w;
-                count += __popc(m);
-            }
+            uint32_t nz = nzmap[sb * 256 + j];
+            if (TPS == 1) nzmap[sb * 256 + j] = 0;
             while (nz) {
                 const int w = __ffs(nz) - 1;
                 nz &= nz - 1;
                 uint32_t* mp = &mask[(sb * UT_RW + w) * 256 + j];
                 uint32_t mm = *mp;
+                count += __popc(mm);
                 if (TPS == 1) *mp = 0;   // this thread is the word's only reader: clear it for the next tile
                 while (mm) {
                     const uint32_t rr = (uint32_t)(w * 32 + __ffs(mm) - 1);
@@ -360,6 +362,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_update_tiles(const __grid_con
         }
         __syncthreads();   // the tile and the masks may be overwritten
         if (TPS > 1) {     // several threads read each mask word: clear them together
+            for (int t = tid; t < 4 * 256; t += UT_THREADS) nzmap[t] = 0;
             for (int t = tid; t < G * UT_RW * 256 / 4; t += UT_THREADS) reinterpret_cast<uint4*>(mask)[t] = make_uint4(0, 0, 0, 0);
             __syncthreads();
         }
