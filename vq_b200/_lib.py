@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvqb200.so")
+# VQB200_LIB: a differently built library (A/B timings of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("VQB200_LIB") or os.path.join(HERE, "libvqb200.so")
 
 SUCCESS, ERR_NULL_PTR, ERR_EMPTY_INPUT, ERR_INVALID_INPUT = 0, -1, -2, -3
 ERR_UNSUPPORTED_DEVICE, ERR_DIM_MISMATCH, FAILURE = -4, -5, -99

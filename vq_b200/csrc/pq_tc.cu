@@ -48,6 +48,12 @@
 
 namespace {
 
+#ifndef VQB_SPIN_FULL
+#define VQB_SPIN_FULL 32
+#endif
+#ifndef VQB_SPIN_EMPTY
+#define VQB_SPIN_EMPTY 32
+#endif
 constexpr int TC_N = 256;          // MMA N = centroid slots per subspace
 constexpr int TC_ROWS = 128;       // MMA M = rows per tile = TMEM lanes
 constexpr int RAW_STAGES = 3;      // TMA -> everyone: raw fp32 row tiles (128 rows x 128 B, SWIZZLE_128B)
@@ -146,6 +152,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
+    if (SLEEP_NS == 0) { while (!mbar_try(bar, parity)) { } return; }
     do { __nanosleep(SLEEP_NS); } while (!mbar_try(bar, parity));
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -521,7 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 for (int i = 0; i < g_cnt; ++i) {
                     if (!(act_mask >> i & 1)) continue;
                     const int acc = u & 1, cph = (u >> 1) & 1;
-                    mbar_wait<32>(ACC_EMPTY(acc), cph ^ 1);
+                    mbar_wait<VQB_SPIN_EMPTY>(ACC_EMPTY(acc), cph ^ 1);
                     tc_fence_after();
                     // K = 8 step j of the sub-vector: 32 bytes further along the 128-byte row (A), two 16-byte chunks
                     // further in the B image
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_assign(const __grid_consta
                 const int rs = u % RES_STAGES, rph = (u / RES_STAGES) & 1;
                 ++u;
 
-                mbar_wait<32>(ACC_FULL(acc), cph);
+                mbar_wait<VQB_SPIN_FULL>(ACC_FULL(acc), cph);
                 tc_fence_after();
                 const bool stamp = DEBUG && p.dbg_ts && blockIdx.x == 0 && r == 0 && (int)(u - 1) < p.dbg_ts_units;
                 if (stamp) p.dbg_ts[(u - 1) * 8 + 2] = clock64();
