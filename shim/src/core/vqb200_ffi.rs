@@ -30,6 +30,8 @@ pub const VQB_ASSIGN_EXACT: u32 = 1;
 pub const VQB_ASSIGN_TENSOR: u32 = 2;
 pub const VQB_TRAIN_USE_COMM: u32 = 1;
 pub const VQB_COMM_ID_BYTES: usize = 128;
+/// EXTENSION metric id (max_i |a_i - b_i|): not a variant of the crate's `Distance` (src/core/distance.rs:8-17).
+pub const VQB_CHEBYSHEV: c_int = 5;
 
 #[repr(C)]
 pub struct VqbTrainOpts {

@@ -83,7 +83,8 @@ def test_callback_typedefs_and_constants_match():
     assert re.search(r"fn\(user: \*mut c_void, buf: \*mut f32, count: usize, cuda_stream: \*mut c_void\) -> c_int", rs)
     for cname, rname in (("VQB_UPDATE_ORDERED", "VQB_UPDATE_ORDERED"), ("VQB_UPDATE_FAST", "VQB_UPDATE_FAST"),
                          ("VQB_ASSIGN_AUTO", "VQB_ASSIGN_AUTO"), ("VQB_ASSIGN_EXACT", "VQB_ASSIGN_EXACT"),
-                         ("VQB_ASSIGN_TENSOR", "VQB_ASSIGN_TENSOR"), ("VQB_COMM_ID_BYTES", "VQB_COMM_ID_BYTES")):
+                         ("VQB_ASSIGN_TENSOR", "VQB_ASSIGN_TENSOR"), ("VQB_COMM_ID_BYTES", "VQB_COMM_ID_BYTES"),
+                         ("VQB_CHEBYSHEV", "VQB_CHEBYSHEV")):
         cv = int(re.search(rf"#define {cname}\s+(\d+)", hdr).group(1))
         rv = int(re.search(rf"pub const {rname}: \w+ = (\d+);", rs).group(1))
         assert cv == rv, cname
