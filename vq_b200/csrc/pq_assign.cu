@@ -151,8 +151,14 @@ int launch_mk(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t k, size
         VQB_AS_CASE(2)
         VQB_AS_CASE(4)
         VQB_AS_CASE(8)
+        VQB_AS_CASE(12)
         VQB_AS_CASE(16)
+        VQB_AS_CASE(20)
+        VQB_AS_CASE(24)
         VQB_AS_CASE(32)
+        VQB_AS_CASE(40)
+        VQB_AS_CASE(48)
+        VQB_AS_CASE(64)
         default: {
             auto kern = k_assign_exact<MK, 0>;
             VQB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
