@@ -207,42 +207,66 @@ k_colsum_w(const float* __restrict__ x, int dim, const uint32_t* __restrict__ pe
 // producer warps.  The chain's dependent FADD (4 cycles a row) is the floor there, so the accumulating warp does
 // nothing else: producers gather the rows with cp.async into a 16-stage ring and publish each tile through a
 // shared-memory sequence word; the consumer publishes its progress so a stage is only overwritten once read.
-constexpr int CP_STAGES = 16, CP_PROD = 7, CP_DEPTH = 2;  // per producer: CP_DEPTH tiles in flight (14 of 16 stages)
-template <int MODE>
+//
+// ROWS x STAGES: the tile size and ring depth.  Removing the loads or the chain from this kernel leaves most of its time
+// (experiment of round 2: 23.7 ms for a depth-1 build, 22.7 ms with the producers' loads skipped, 18.9 ms with the
+// consumer's chain skipped): on the few-node levels the publish / poll / progress hand-shake per 32-row tile is the cost, not
+// memory or the dependent adds.  Levels with at most one CTA per SM therefore use 128-row tiles (a quarter of the hand-shakes
+// per row, 12 x 16 KB stages), levels with at most two CTAs per SM 64-row tiles (12 x 8 KB); the rest keep 32 x 16.
+constexpr int CP_PROD = 7;
+template <int MODE, int ROWS, int STAGES, int DEPTH>
 __global__ void __launch_bounds__((CP_PROD + 1) * 32)
 k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm, const NodeSeg* __restrict__ nodes,
             const float* __restrict__ mean, float* __restrict__ out, int n_slices) {
+    constexpr int SB = ROWS / 32;                  // 32-row batches per tile
     extern __shared__ __align__(16) float ring[];  // [stage][row][32]
-    __shared__ volatile uint32_t full[CP_STAGES];  // tile index + 1 that currently fills the stage
+    __shared__ volatile uint32_t full[STAGES];     // tile index + 1 that currently fills the stage
     __shared__ volatile uint32_t done;             // tiles the consumer has finished
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned node = blockIdx.x / n_slices;
     const int col0 = (int)(blockIdx.x % n_slices) * CS_SLICE;
     const NodeSeg ns = nodes[node];
     const uint32_t* ids = perm + ns.beg;
-    const int n_tiles = (int)((ns.len + CW_ROWS - 1) / CW_ROWS);
-    if (threadIdx.x < CP_STAGES) full[threadIdx.x] = 0;
+    const int n_tiles = (int)((ns.len + ROWS - 1) / ROWS);
+    if (threadIdx.x < STAGES) full[threadIdx.x] = 0;
     if (threadIdx.x == 0) done = 0;
     __syncthreads();
 
     if (warp == 0) {
-        // ---- consumer: the chain
+        // ---- consumer: the chain.  Inside a tile the 32 values of the next batch are loaded into a second register array
+        // before the current batch's dependent adds start (4 cycles each, three issue slots in four free), so only the first
+        // batch of a tile waits for shared memory.
         float acc = 0.0f, mu = 0.0f;
         if (MODE == 1) mu = mean[(size_t)node * dim + col0 + lane];
+        auto load32 = [&](const float* base, float (&dst)[32]) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) dst[r] = base[r * CS_SLICE];
+        };
+        auto chain32 = [&](const float (&src)[32]) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                if (MODE == 0) acc = __fadd_rn(acc, src[r]);
+                else { const float df = __fsub_rn(src[r], mu); acc = __fadd_rn(acc, __fmul_rn(df, df)); }
+            }
+        };
         for (int t = 0; t < n_tiles; ++t) {
-            const int stg = t % CP_STAGES;
+            const int stg = t % STAGES;
             while (full[stg] != (uint32_t)(t + 1)) { }
             __syncwarp();
-            const float* st = ring + (size_t)stg * CW_ROWS * CS_SLICE + lane;
-            const int rows = min(CW_ROWS, (int)ns.len - t * CW_ROWS);
-            if (rows == CW_ROWS) {
-                float v[CW_ROWS];
+            const float* st = ring + (size_t)stg * ROWS * CS_SLICE + lane;
+            const int rows = min(ROWS, (int)ns.len - t * ROWS);
+            if (rows == ROWS) {
+                float va[32], vb[32];
+                load32(st, va);
+                if (SB == 1) chain32(va);
+                else {
 #pragma unroll
-                for (int r = 0; r < CW_ROWS; ++r) v[r] = st[r * CS_SLICE];
-#pragma unroll
-                for (int r = 0; r < CW_ROWS; ++r) {
-                    if (MODE == 0) acc = __fadd_rn(acc, v[r]);
-                    else { const float df = __fsub_rn(v[r], mu); acc = __fadd_rn(acc, __fmul_rn(df, df)); }
+                    for (int b = 0; b < SB; b += 2) {
+                        load32(st + (size_t)(b + 1) * 32 * CS_SLICE, vb);
+                        chain32(va);
+                        if (b + 2 < SB) load32(st + (size_t)(b + 2) * 32 * CS_SLICE, va);
+                        chain32(vb);
+                    }
                 }
             } else {
                 for (int r = 0; r < rows; ++r) {
@@ -265,31 +289,43 @@ k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ p
             const int tile = p + i * CP_PROD;
             __syncwarp();
             __threadfence_block();
-            if (lane == 0) full[tile % CP_STAGES] = (uint32_t)(tile + 1);
+            if (lane == 0) full[tile % STAGES] = (uint32_t)(tile + 1);
         };
-        uint32_t idv_next = (p * CW_ROWS + lane < (int)ns.len) ? __ldg(ids + p * CW_ROWS + lane) : 0u;
+        auto fetch_ids = [&](long long r0, uint32_t (&idv)[SB]) {   // lane l holds rows r0 + 32 b + l
+#pragma unroll
+            for (int b = 0; b < SB; ++b) {
+                const long long rn = r0 + 32 * b + lane;
+                idv[b] = rn < (long long)ns.len ? __ldg(ids + rn) : 0u;
+            }
+        };
+        uint32_t idv_next[SB];
+        fetch_ids((long long)p * ROWS, idv_next);
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = p + i * CP_PROD;
-            const int r0 = tile * CW_ROWS;
-            const int rows = min(CW_ROWS, (int)ns.len - r0);
-            const uint32_t idv = idv_next;
-            const long long rn = (long long)r0 + CP_PROD * CW_ROWS + lane;
-            idv_next = rn < (long long)ns.len ? __ldg(ids + rn) : 0u;
-            // the stage's previous tile must have been consumed (plain polling: a measured nanosleep back-off here made
-            // the first levels 15 % slower -- they are bound by how early the gathers are issued, not by the chain)
-            if (tile >= CP_STAGES) while ((int)done < tile - CP_STAGES + 1) { }
-            float* st = ring + (size_t)(tile % CP_STAGES) * CW_ROWS * CS_SLICE;
+            const int r0 = tile * ROWS;
+            const int rows = min(ROWS, (int)ns.len - r0);
+            uint32_t idv[SB];
 #pragma unroll
-            for (int q = 0; q < CW_ROWS / 4; ++q) {
-                const int r = q * 4 + sub;
-                const uint32_t id = __shfl_sync(0xFFFFFFFFu, idv, r);
-                if (r < rows) cp_async16(st + r * CS_SLICE + part, x + (size_t)id * dim + col0 + part);
+            for (int b = 0; b < SB; ++b) idv[b] = idv_next[b];
+            fetch_ids((long long)r0 + (long long)CP_PROD * ROWS, idv_next);
+            // the stage's previous tile must have been consumed (plain polling: a measured nanosleep back-off here made
+            // the first levels 15 % slower)
+            if (tile >= STAGES) while ((int)done < tile - STAGES + 1) { }
+            float* st = ring + (size_t)(tile % STAGES) * ROWS * CS_SLICE;
+#pragma unroll
+            for (int b = 0; b < SB; ++b) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int r = b * 32 + q * 4 + sub;
+                    const uint32_t id = __shfl_sync(0xFFFFFFFFu, idv[b], q * 4 + sub);
+                    if (r < rows) cp_async16(st + r * CS_SLICE + part, x + (size_t)id * dim + col0 + part);
+                }
             }
             cp_async_commit();
-            if (i >= CP_DEPTH) { cp_async_wait<CP_DEPTH>(); publish(i - CP_DEPTH); }
+            if (i >= DEPTH) { cp_async_wait<DEPTH>(); publish(i - DEPTH); }
         }
         cp_async_wait<0>();
-        for (int i = max(0, my_tiles - CP_DEPTH); i < my_tiles; ++i) publish(i);
+        for (int i = max(0, my_tiles - DEPTH); i < my_tiles; ++i) publish(i);
     }
 }
 
@@ -796,8 +832,20 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<0, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
     VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_w<1, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
     const unsigned cta_slots = (unsigned)ctx->sm_count * 3;  // 64 KB CTAs resident at once
-    VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum_pc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
-    VQB_CUDA(ctx, cudaFuncSetAttribute(k_colsum_pc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM));
+    constexpr int PC_SMEM_128 = 12 * 128 * CS_SLICE * 4, PC_SMEM_64 = 12 * 64 * CS_SLICE * 4;
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<0, 32, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<1, 32, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<0, 64, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_64)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<1, 64, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_64)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<0, 128, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_128)));
+    VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<1, 128, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_128)));
+    static const int pc_force = [] { const char* e = std::getenv("VQB_TSVQ_PC_ROWS"); return e ? std::atoi(e) : 0; }();
+    auto pc_rows = [&](unsigned ctas) -> int {   // tile rows of the producer / consumer kernel for a level of `ctas` CTAs
+        if (pc_force == 32 || pc_force == 64 || pc_force == 128) return pc_force;
+        if (ctas <= (unsigned)ctx->sm_count) return 128;
+        if (ctas <= 2u * (unsigned)ctx->sm_count) return 64;
+        return 32;
+    };
     static const bool old_colsum = [] { const char* e = std::getenv("VQB_TSVQ_OLD_COLSUM"); return e && *e && *e != '0'; }();
     const bool warp_chains = vec_ok && dim % CS_SLICE == 0 && !old_colsum;  // else: block-wide ring kernel (any dim / alignment)
     const int n_slices = (int)(dim / CS_SLICE);
@@ -856,9 +904,12 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         if (gcs.y > 65535) return vqb_fail(ctx, VQB_ERR_INVALID_INPUT, "too many nodes on one level");
         if (warp_chains) {
             const unsigned tw = (unsigned)(ln * n_slices);
-            if (tw <= 2 * cta_slots)
-                k_colsum_pc<0><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
-            else
+            if (tw <= 2 * cta_slots) {
+                const int pr = pc_rows(tw);
+                if (pr == 128) k_colsum_pc<0, 128, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_128, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
+                else if (pr == 64) k_colsum_pc<0, 64, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_64, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
+                else k_colsum_pc<0, 32, 16, 2><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
+            } else
                 k_colsum_w<0, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
         } else
         k_colsum<0><<<gcs, CS_THREADS, CS_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr,
@@ -907,9 +958,12 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
         dim3 gvs(cdiv(dim, CS_SLICE), (unsigned)sn);
         if (warp_chains) {
             const unsigned tw = (unsigned)(sn * n_slices);
-            if (tw <= 2 * cta_slots)
-                k_colsum_pc<1><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
-            else
+            if (tw <= 2 * cta_slots) {
+                const int pr = pc_rows(tw);
+                if (pr == 128) k_colsum_pc<1, 128, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_128, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
+                else if (pr == 64) k_colsum_pc<1, 64, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_64, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
+                else k_colsum_pc<1, 32, 16, 2><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
+            } else
                 k_colsum_w<1, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
         } else
         k_colsum<1><<<gvs, CS_THREADS, CS_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(),
