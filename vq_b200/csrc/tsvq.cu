@@ -212,13 +212,15 @@ k_colsum_w(const float* __restrict__ x, int dim, const uint32_t* __restrict__ pe
 // (experiment of round 2: 23.7 ms for a depth-1 build, 22.7 ms with the producers' loads skipped, 18.9 ms with the
 // consumer's chain skipped): on the few-node levels the publish / poll / progress hand-shake per 32-row tile is the cost, not
 // memory or the dependent adds.  Levels with at most one CTA per SM therefore use 128-row tiles (a quarter of the hand-shakes
-// per row, 12 x 16 KB stages), levels with at most two CTAs per SM 64-row tiles (12 x 8 KB); the rest keep 32 x 16.
+// per row, 12 x 16 KB stages), the other levels this kernel serves 64-row tiles (12 x 8 KB).  The ring needs at least
+// producers x DEPTH + 1 stages (a producer publishes tile i only after issuing tile i + DEPTH: 6 stages dead-lock).
 constexpr int CP_PROD = 7;
 template <int MODE, int ROWS, int STAGES, int DEPTH>
 __global__ void __launch_bounds__((CP_PROD + 1) * 32)
 k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm, const NodeSeg* __restrict__ nodes,
             const float* __restrict__ mean, float* __restrict__ out, int n_slices) {
     constexpr int SB = ROWS / 32;                  // 32-row batches per tile
+    static_assert(STAGES >= CP_PROD * DEPTH + 1, "ring too shallow: a producer issues tile i + DEPTH before it publishes tile i, so it would wait for a stage whose tile it has not published");
     extern __shared__ __align__(16) float ring[];  // [stage][row][32]
     __shared__ volatile uint32_t full[STAGES];     // tile index + 1 that currently fills the stage
     __shared__ volatile uint32_t done;             // tiles the consumer has finished
@@ -843,8 +845,7 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     auto pc_rows = [&](unsigned ctas) -> int {   // tile rows of the producer / consumer kernel for a level of `ctas` CTAs
         if (pc_force == 32 || pc_force == 64 || pc_force == 128) return pc_force;
         if (ctas <= (unsigned)ctx->sm_count) return 128;
-        if (ctas <= 2u * (unsigned)ctx->sm_count) return 64;
-        return 32;
+        return 64;   // measured per level (1M x 1536): 64-row tiles beat 32-row ones on every level this kernel serves
     };
     static const bool old_colsum = [] { const char* e = std::getenv("VQB_TSVQ_OLD_COLSUM"); return e && *e && *e != '0'; }();
     const bool warp_chains = vec_ok && dim % CS_SLICE == 0 && !old_colsum;  // else: block-wide ring kernel (any dim / alignment)
