@@ -218,8 +218,9 @@ constexpr int CP_PROD = 7;
 template <int MODE, int ROWS, int STAGES, int DEPTH>
 __global__ void __launch_bounds__((CP_PROD + 1) * 32)
 k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ perm, const NodeSeg* __restrict__ nodes,
-            const float* __restrict__ mean, float* __restrict__ out, int n_slices) {
+            const float* __restrict__ mean, float* __restrict__ out, int n_slices, int sleep_ns) {
     constexpr int SB = ROWS / 32;                  // 32-row batches per tile
+    const int nprod = (int)(blockDim.x >> 5) - 1;  // producer warps of this launch (<= CP_PROD)
     static_assert(STAGES >= CP_PROD * DEPTH + 1, "ring too shallow: a producer issues tile i + DEPTH before it publishes tile i, so it would wait for a stage whose tile it has not published");
     extern __shared__ __align__(16) float ring[];  // [stage][row][32]
     __shared__ volatile uint32_t full[STAGES];     // tile index + 1 that currently fills the stage
@@ -286,9 +287,9 @@ k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ p
         // ---- producers: tiles p, p + CP_PROD, p + 2 CP_PROD, ...; row ids fetched one tile ahead
         const int p = warp - 1;
         const int sub = lane >> 3, part = (lane & 7) * 4;
-        const int my_tiles = (n_tiles - p + CP_PROD - 1) / CP_PROD;
+        const int my_tiles = (n_tiles - p + nprod - 1) / nprod;
         auto publish = [&](int i) {  // this producer's i-th tile has landed
-            const int tile = p + i * CP_PROD;
+            const int tile = p + i * nprod;
             __syncwarp();
             __threadfence_block();
             if (lane == 0) full[tile % STAGES] = (uint32_t)(tile + 1);
@@ -303,16 +304,16 @@ k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ p
         uint32_t idv_next[SB];
         fetch_ids((long long)p * ROWS, idv_next);
         for (int i = 0; i < my_tiles; ++i) {
-            const int tile = p + i * CP_PROD;
+            const int tile = p + i * nprod;
             const int r0 = tile * ROWS;
             const int rows = min(ROWS, (int)ns.len - r0);
             uint32_t idv[SB];
 #pragma unroll
             for (int b = 0; b < SB; ++b) idv[b] = idv_next[b];
-            fetch_ids((long long)r0 + (long long)CP_PROD * ROWS, idv_next);
+            fetch_ids((long long)r0 + (long long)nprod * ROWS, idv_next);
             // the stage's previous tile must have been consumed (plain polling: a measured nanosleep back-off here made
             // the first levels 15 % slower)
-            if (tile >= STAGES) while ((int)done < tile - STAGES + 1) { }
+            if (tile >= STAGES) while ((int)done < tile - STAGES + 1) { if (sleep_ns) __nanosleep(sleep_ns); }
             float* st = ring + (size_t)(tile % STAGES) * ROWS * CS_SLICE;
 #pragma unroll
             for (int b = 0; b < SB; ++b) {
@@ -841,6 +842,8 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
     VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<1, 64, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_64)));
     VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<0, 128, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_128)));
     VQB_CUDA(ctx, (cudaFuncSetAttribute(k_colsum_pc<1, 128, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_128)));
+    static const int pc_prod = [] { const char* e = std::getenv("VQB_TSVQ_PROD"); int v = e ? std::atoi(e) : 3; return v >= 1 && v <= CP_PROD ? v : 3; }();   // 3 producer warps: 28.6 ms against 31.3 with 7 (1M x 1536, depth 8)
+    static const int pc_sleep = [] { const char* e = std::getenv("VQB_TSVQ_PSLEEP"); return e ? std::atoi(e) : 0; }();
     static const int pc_force = [] { const char* e = std::getenv("VQB_TSVQ_PC_ROWS"); return e ? std::atoi(e) : 0; }();
     auto pc_rows = [&](unsigned ctas) -> int {   // tile rows of the producer / consumer kernel for a level of `ctas` CTAs
         if (pc_force == 32 || pc_force == 64 || pc_force == 128) return pc_force;
@@ -907,9 +910,9 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
             const unsigned tw = (unsigned)(ln * n_slices);
             if (tw <= 2 * cta_slots) {
                 const int pr = pc_rows(tw);
-                if (pr == 128) k_colsum_pc<0, 128, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_128, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
-                else if (pr == 64) k_colsum_pc<0, 64, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_64, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
-                else k_colsum_pc<0, 32, 16, 2><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices);
+                if (pr == 128) k_colsum_pc<0, 128, 12, 1><<<tw, (pc_prod + 1) * 32, PC_SMEM_128, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, pc_sleep);
+                else if (pr == 64) k_colsum_pc<0, 64, 12, 1><<<tw, (pc_prod + 1) * 32, PC_SMEM_64, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, pc_sleep);
+                else k_colsum_pc<0, 32, 16, 2><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, 0);
             } else
                 k_colsum_w<0, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_segs.as<NodeSeg>(), nullptr, d_mean.as<float>(), n_slices, tw);
         } else
@@ -961,9 +964,9 @@ int vqb_tsvq_train(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t ma
             const unsigned tw = (unsigned)(sn * n_slices);
             if (tw <= 2 * cta_slots) {
                 const int pr = pc_rows(tw);
-                if (pr == 128) k_colsum_pc<1, 128, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_128, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
-                else if (pr == 64) k_colsum_pc<1, 64, 12, 1><<<tw, (CP_PROD + 1) * 32, PC_SMEM_64, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
-                else k_colsum_pc<1, 32, 16, 2><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices);
+                if (pr == 128) k_colsum_pc<1, 128, 12, 1><<<tw, (pc_prod + 1) * 32, PC_SMEM_128, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, pc_sleep);
+                else if (pr == 64) k_colsum_pc<1, 64, 12, 1><<<tw, (pc_prod + 1) * 32, PC_SMEM_64, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, pc_sleep);
+                else k_colsum_pc<1, 32, 16, 2><<<tw, (CP_PROD + 1) * 32, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, 0);
             } else
                 k_colsum_w<1, 4, 4><<<cdiv(tw, 4), 128, CW_SMEM, st>>>(xd, (int)dim, perm, d_ssegs.as<NodeSeg>(), d_smean.as<float>(), d_var.as<float>(), n_slices, tw);
         } else
