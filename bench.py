@@ -366,7 +366,7 @@ def measure_paths(eng, ext, x, pq, peaks):
         # single-vector quantize, the reference's own call shape (src/pq.rs:167; loop at src/bin/eval_pq.rs:53-58)
         v1 = np.ascontiguousarray(x[:1].cpu().numpy()); o1 = np.empty(dim, np.float16)
         t = wall(lambda: eng.check(lib.vqb_pq_encode(pq._handle, v1.ctypes.data, 1, 0, None, 1, o1.ctypes.data)), reps=200)
-        e2e["pq_quantize_single_vector"] = {"us_per_call": t * 1e6, "note": "host f32[768] in, f16[768] out, exact CUDA-core kernel (n < 1024)"}
+        e2e["pq_quantize_single_vector"] = {"us_per_call": t * 1e6, "note": "host f32[768] in, f16[768] out, warp-per-(row, subspace) CUDA-core kernel (n <= 64), single-stream small-call path"}
         res["host_buffers"] = e2e
     except Exception as ex:
         res["host_buffers"] = {"error": repr(ex)[:200]}

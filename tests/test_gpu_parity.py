@@ -357,6 +357,32 @@ def test_pq_encode_kernel_selection_sweep(vq, oracle, metric, sub_dim, k, n):
     assert np.array_equal(recon_d.cpu().numpy().view(np.uint16), want_recon.view(np.uint16))
 
 
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("sub_dim,k", [(4, 256), (8, 256), (13, 50), (24, 300), (1, 7)])
+def test_pq_encode_a_handful_of_rows(vq, oracle, metric, sub_dim, k):
+    """The reference's call shape is one vector per call (src/pq.rs:167): up to 64 rows take the warp-per-(row, subspace)
+    kernel.  Codes and reconstructions identical with the oracle for n = 1 ... 65, with NaN / zero / duplicate cases."""
+    m = 3
+    dim = m * sub_dim
+    base = mixture(400, dim, 900 + sub_dim)
+    rng = np.random.default_rng(901 + sub_dim)
+    cb = np.stack([base[rng.choice(400, k, replace=k > 400), s * sub_dim:(s + 1) * sub_dim] for s in range(m)]).astype(F)
+    cb[0, min(3, k - 1)] = cb[0, 1]          # duplicate: lowest index wins
+    cb[m - 1, 0] = 0.0
+    pq = vq.ProductQuantizer.from_codebooks(cb, vq.Distance(metric))
+    for n in (1, 2, 5, 33, 64, 65):
+        x = mixture(n, dim, 950 + n)
+        x[0, :sub_dim] = np.nan if n > 1 else x[0, :sub_dim]
+        if n > 2: x[2] = 0.0
+        if n > 4: x[4, :sub_dim] = cb[0, 1]
+        codes, recon = pq.encode_with_recon(x)
+        want_codes, want_recon = oracle.pq_encode(cb, metric, x, sem="avx512")
+        assert np.array_equal(codes.astype(np.uint32), want_codes), n
+        assert np.array_equal(bits(recon), bits(want_recon)), n
+    q = pq.quantize(base[7])
+    assert np.array_equal(bits(q), bits(oracle.pq_encode(cb, metric, base[7:8], sem="avx512")[1][0]))
+
+
 def test_pq_encode_vs_real_hsdlib_near_tie_rule(vq, oracle):
     """Against hsdlib compiled verbatim from the reference, whatever this host dispatches to:
     >= 99.9 % agreement and every disagreement within 1e-5 relative distance."""

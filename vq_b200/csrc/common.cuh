@@ -220,6 +220,23 @@ int vqb_chunk_pipeline(vqb_ctx* ctx, size_t n, const ChunkIo& io, Launch&& launc
     const size_t widest = std::max(std::max(io.in_unit, io.out0 ? io.out0_unit : 0), std::max<size_t>(io.out1 ? io.out1_unit : 0, 1));
     size_t chunk = std::max<size_t>(1, vqb_chunk_bytes() / widest);
     chunk = std::min(chunk, n);
+    if (chunk == n && n * widest <= (size_t)256 * 1024) {
+        // small call (the reference's single-vector quantize): nothing to overlap -- upload, kernels and downloads in
+        // order on the context stream, one synchronisation, no events and no second / third stream
+        void *s_in = nullptr, *s0 = nullptr, *s1 = nullptr;
+        if (!in_dev) VQB_CUDA(ctx, vqb_stage(ctx, 0, n * io.in_unit, &s_in));
+        if (io.out0 && !o0_dev) VQB_CUDA(ctx, vqb_stage(ctx, 2, n * io.out0_unit, &s0));
+        if (io.out1 && !o1_dev) VQB_CUDA(ctx, vqb_stage(ctx, 4, n * io.out1_unit, &s1));
+        struct Drain1 { vqb_ctx* c; ~Drain1() { cudaStreamSynchronize(c->stream); } } drain1{ctx};
+        const void* din = io.in;
+        if (!in_dev) { VQB_CUDA(ctx, cudaMemcpyAsync(s_in, io.in, n * io.in_unit, cudaMemcpyHostToDevice, ctx->stream)); din = s_in; }
+        void* d0 = io.out0 ? (o0_dev ? io.out0 : s0) : nullptr;
+        void* d1 = io.out1 ? (o1_dev ? io.out1 : s1) : nullptr;
+        VQB_TRY(launch(din, d0, d1, n, 0));
+        if (io.out0 && !o0_dev) VQB_CUDA(ctx, cudaMemcpyAsync(io.out0, s0, n * io.out0_unit, cudaMemcpyDeviceToHost, ctx->stream));
+        if (io.out1 && !o1_dev) VQB_CUDA(ctx, cudaMemcpyAsync(io.out1, s1, n * io.out1_unit, cudaMemcpyDeviceToHost, ctx->stream));
+        return VQB_SUCCESS;   // ~Drain1 synchronises the stream
+    }
     for (int i = 0; i < 7; ++i)
         if (!ctx->stage_ev[i]) VQB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
     void *sin[2] = {nullptr, nullptr}, *so0[2] = {nullptr, nullptr}, *so1[2] = {nullptr, nullptr};

@@ -127,10 +127,71 @@ k_assign_exact(const float* __restrict__ x, size_t n, int dim, int k, int sub_di
     }
 }
 
+// A handful of rows (the reference's call shape is ONE vector per quantize call, src/pq.rs:167): the kernel above would run
+// one live thread per CTA through all k centroids.  Here a warp serves one (row, subspace) pair, its lanes take the centroids
+// j = lane, lane + 32, ... with the same evaluation functions, and the warp keeps the reference's choice: index 0 seeds the
+// minimum whatever its value, then strict '<' in ascending index order (= smallest distance, lowest index on ties).
+template <int MK>
+__global__ void __launch_bounds__(32)
+k_assign_small(const float* __restrict__ x, int dim, int k, int d, const float* __restrict__ codebooks,
+               void* __restrict__ codes, uint32_t code_bytes, size_t stride_row, size_t stride_sub, __half* __restrict__ recon) {
+    const int lane = threadIdx.x;
+    const size_t row = blockIdx.x;
+    const int s = blockIdx.y;
+    const float* cb = codebooks + (size_t)s * k * d;
+    PtrAcc xp{x + row * (size_t)dim + (size_t)s * d};
+    float na = 0.f, sa = 0.f;
+    bool a_tail_ok = true;
+    if (MK == MK_COSINE) { na = hsd_cosine_norm<0>(xp, d, a_tail_ok); sa = __fsqrt_rn(na); }
+    float bd = __int_as_float(0x7f800000);
+    uint32_t bj = 0xFFFFFFFFu;
+    bool d0nan = false;
+    for (int j = lane; j < k; j += 32) {
+        PtrAcc cp{cb + (size_t)j * d};
+        float dd;
+        if (MK == MK_TRAIN) dd = dist2_seq<0>(xp, cp, d);
+        else if (MK == MK_COSINE) {
+            if (d == 0) dd = 0.f;
+            else {
+                bool tok;
+                const float nb = hsd_cosine_norm<0>(cp, d, tok);
+                const float dot = hsd_cosine_dot<0>(xp, cp, d);
+                bool ok = a_tail_ok && tok;
+                float sim = 0.f;
+                if (ok) sim = hsd_cosine_from_sums(dot, na, nb, sa, __fsqrt_rn(nb), ok);
+                dd = ok ? __fsub_rn(1.0f, sim) : rust_cos<0>(xp, cp, d);
+            }
+        } else dd = vq_distance<0>(MK, xp, cp, d);
+        if (j == 0) d0nan = isnan(dd);
+        if (isnan(dd)) dd = __int_as_float(0x7f800000);
+        if (bj == 0xFFFFFFFFu || dd < bd) { bd = dd; bj = (uint32_t)j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float od = __shfl_xor_sync(0xFFFFFFFFu, bd, off);
+        const uint32_t oj = __shfl_xor_sync(0xFFFFFFFFu, bj, off);
+        if (oj != 0xFFFFFFFFu && (bj == 0xFFFFFFFFu || od < bd || (od == bd && oj < bj))) { bd = od; bj = oj; }
+    }
+    d0nan = __shfl_sync(0xFFFFFFFFu, d0nan ? 1 : 0, 0) != 0;
+    const uint32_t best = d0nan ? 0u : bj;   // vector.rs:354-361 / pq.rs:183-191: a NaN at index 0 is never replaced
+    if (lane == 0 && codes) store_code_any(codes, code_bytes, row * stride_row + (size_t)s * stride_sub, best);
+    if (recon) {  // pq.rs:193-195
+        const float* c = cb + (size_t)best * d;
+        __half* r = recon + row * (size_t)dim + (size_t)s * d;
+        for (int i = lane; i < d; i += 32) r[i] = __float2half_rn(__ldg(c + i));
+    }
+}
+
 template <int MK>
 int launch_mk(vqb_ctx* ctx, const float* x, size_t n, size_t dim, size_t k, size_t d, const float* cb,
               const int* sub_list, int n_sub, void* codes, uint32_t code_bytes, size_t stride_row,
               size_t stride_sub, __half* recon, const int* n_sub_dev, const uint32_t* go) {
+    if (n <= 64 && !sub_list && !n_sub_dev && !go && (size_t)n_sub <= 65535) {   // a few rows: warp per (row, subspace)
+        k_assign_small<MK><<<dim3((unsigned)n, (unsigned)n_sub), 32, 0, ctx->stream>>>(x, (int)dim, (int)k, (int)d, cb, codes, code_bytes,
+                                                                                   stride_row, stride_sub, recon);
+        VQB_LAUNCHED(ctx);
+        return VQB_SUCCESS;
+    }
     // centroid chunk that fits a 96 KB dynamic smem budget
     size_t per = d * sizeof(float) + (MK == MK_COSINE ? sizeof(CosAux) : 0);
     if (per == 0) per = 4;
