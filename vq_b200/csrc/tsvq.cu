@@ -264,11 +264,21 @@ k_colsum_pc(const float* __restrict__ x, int dim, const uint32_t* __restrict__ p
                 if (SB == 1) chain32(va);
                 else {
 #pragma unroll
+                    // one load of the next batch behind every dependent add of the running one (the add has a 4-cycle latency,
+                    // the load fills one of the free issue slots)
+                    auto chain_load = [&](const float (&src)[32], float (&dst)[32], const float* nxt) {
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            if (MODE == 0) acc = __fadd_rn(acc, src[r]);
+                            else { const float df = __fsub_rn(src[r], mu); acc = __fadd_rn(acc, __fmul_rn(df, df)); }
+                            dst[r] = nxt[r * CS_SLICE];
+                        }
+                    };
+#pragma unroll
                     for (int b = 0; b < SB; b += 2) {
-                        load32(st + (size_t)(b + 1) * 32 * CS_SLICE, vb);
-                        chain32(va);
-                        if (b + 2 < SB) load32(st + (size_t)(b + 2) * 32 * CS_SLICE, va);
-                        chain32(vb);
+                        chain_load(va, vb, st + (size_t)(b + 1) * 32 * CS_SLICE);
+                        if (b + 2 < SB) chain_load(vb, va, st + (size_t)(b + 2) * 32 * CS_SLICE);
+                        else chain32(vb);
                     }
                 }
             } else {
