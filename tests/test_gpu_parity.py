@@ -351,7 +351,10 @@ def test_pq_encode_kernel_selection_sweep(vq, oracle, metric, sub_dim, k, n):
     codes, recon = pq.encode_with_recon(x)
     assert np.array_equal(codes.astype(np.uint32), want_codes)
     assert np.array_equal(bits(recon), bits(want_recon))
+    # decode (tiled kernel for u8 codes, sub_dim 4 / 8 / 16 / 32, n >= 4096; gather kernel otherwise) == f16 round trip
+    assert np.array_equal(bits(pq.decode(codes)), bits(want_recon.astype(F)))
     xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(bits(pq.decode(torch.from_numpy(codes).cuda()).cpu().numpy()), bits(want_recon.astype(F)))
     codes_d, recon_d = pq.encode_with_recon(xd)
     assert np.array_equal(codes_d.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, want_codes.astype(np.int64))
     assert np.array_equal(recon_d.cpu().numpy().view(np.uint16), want_recon.view(np.uint16))
