@@ -97,6 +97,11 @@ def test_pq_tsvq_validation_order_and_messages():
         vq.Distance("chebyshev")  # not a variant of the reference's Distance (src/core/distance.rs:8-17)
     assert vq.Distance("SquaredEuclidean").name() == "squared_euclidean"
     assert repr(vq.Distance.cosine()) == "Distance(metric=cosine)"
+    # the Chebyshev extension is reachable through its own constructor only, with the header's id
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vqb200.h")).read()
+    assert vq.Distance.chebyshev().id == int(re.search(r"#define VQB_CHEBYSHEV\s+(\d+)", hdr).group(1)) == 5
+    assert [vq.Distance(n).id for n in ("squared_euclidean", "euclidean", "manhattan", "cosine")] == [0, 1, 2, 3]
 
 
 # ---------------------------------------------------------------- index stream
