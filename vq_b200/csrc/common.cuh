@@ -206,7 +206,7 @@ struct ChunkIo {
     void* out1 = nullptr;      size_t out1_unit = 0;   // may be null
 };
 inline size_t vqb_chunk_bytes() {
-    static const size_t mb = [] { const char* e = std::getenv("VQB_CHUNK_MB"); long v = e ? std::atol(e) : 0; return (size_t)(v > 0 ? v : 64); }();
+    static const size_t mb = [] { const char* e = std::getenv("VQB_CHUNK_MB"); long v = e ? std::atol(e) : 0; return (size_t)(v > 0 ? v : 32); }();
     return mb << 20;
 }
 template <typename Launch>   // int launch(const void* in_dev, void* out0_dev, void* out1_dev, size_t units, size_t unit0)
@@ -216,7 +216,7 @@ int vqb_chunk_pipeline(vqb_ctx* ctx, size_t n, const ChunkIo& io, Launch&& launc
     const bool o0_dev = !io.out0 || vqb_is_device_ptr(io.out0);
     const bool o1_dev = !io.out1 || vqb_is_device_ptr(io.out1);
     if (in_dev && o0_dev && o1_dev) return launch(io.in, io.out0, io.out1, n, 0);   // all on the device: one asynchronous enqueue
-    // chunk = 64 MB of the widest of the three streams of bytes (decode grows 32-fold on the way out)
+    // chunk = 32 MB of the widest of the three streams of bytes (decode grows 32-fold on the way out)
     const size_t widest = std::max(std::max(io.in_unit, io.out0 ? io.out0_unit : 0), std::max<size_t>(io.out1 ? io.out1_unit : 0, 1));
     size_t chunk = std::max<size_t>(1, vqb_chunk_bytes() / widest);
     chunk = std::min(chunk, n);
