@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 N_ROWS, DIM, M, K = 1_000_000, 768, 96, 256
 ENC_METRIC = "cosine"           # configs[2]: L2 k-means training (src/core/vector.rs:352-363) + cosine encode
 TRAIN_ITERS_FOR_CODEBOOK = 3
-NCU_RAW_CSV = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_tc_assign_ncu_raw.csv")
+NCU_RAW_CSV = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02e_tc_assign_ncu_raw.csv")
 EPILOGUE_CYCLES_PER_UNIT = 576.5    # profiles/r02_ubench.txt (E): scan of one 128-row x 256-centroid unit, 8 warps, nothing else on the SM
 METRIC_NAME = "pq_encode_throughput"
 UNIT = "Mvec/s"
