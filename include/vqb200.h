@@ -147,7 +147,9 @@ typedef int (*vqb_allreduce_fn)(void* user, float* buf, size_t count, void* cuda
 #define VQB_UPDATE_FAST    1 /* fixed-shape partial sums (one pass over X, no second copy): deterministic, not the reference's order */
 #define VQB_ASSIGN_AUTO    0
 #define VQB_ASSIGN_EXACT   1 /* CUDA-core kernel evaluating the reference's formula for every centroid */
-#define VQB_ASSIGN_TENSOR  2 /* tcgen05 GEMM-form scores + exact re-check of the candidates */
+#define VQB_ASSIGN_TENSOR  2 /* tcgen05 GEMM-form scores + exact re-check of the candidates: sub_dim 8, 16, 24 or 32, k <= 256,
+                                 squared L2 / L2 / cosine (and training), 16-byte aligned rows; VQB_ERR_INVALID_INPUT otherwise.
+                                 AUTO takes it from 1024 rows on, and a warp-per-pair kernel for up to 64 rows */
 
 #define VQB_TRAIN_USE_COMM 1u /* flags: rows are sharded over the ranks of the context's communicator (vqb_comm_init_rank);
                                  the per-iteration exchange is one ncclAllReduce issued by the library on the context stream */
